@@ -1,0 +1,236 @@
+/*
+ * fus_b200.h - C ABI of the B200-native (sm_100a) wave-propagation hot path.
+ *
+ * This is the drop-in boundary for fenicsx-fus-gpu's matrix-free explicit
+ * spectral-element path.  The reference has no native ABI of its own: its
+ * device code is Numba @cuda.jit kernels launched from Python
+ * (/root/reference/cuda/operators.py, scatterer.py).  Each entry point below
+ * names the reference kernel / function (file:line) it replaces; the Python
+ * host layer (fenicsx_fus_gpu_b200/operators.py ...) binds them with ctypes
+ * behind the reference's own call surface, see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `stream` is a cudaStream_t passed as
+ *     void* (NULL = legacy default stream);
+ *   - unless a name ends in `_host`, every data pointer is a DEVICE pointer
+ *     owned by the caller; nothing is allocated or freed behind its back;
+ *   - launches are asynchronous on `stream`; ordering is stream ordering, as
+ *     with the reference's Numba launches;
+ *   - return value 0 on success, otherwise a cudaError_t value (or
+ *     FUS_ERR_* below); fus_last_error() gives the text.  Never throws.
+ *   - `_f32` / `_f64` select the float type (the reference's `float_type`).
+ *   - `P` is the polynomial degree, 2..7; n = P+1; Nd = n^3.
+ */
+#ifndef FUS_B200_H
+#define FUS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FUS_ABI_VERSION 1
+
+/* error codes outside the cudaError_t range */
+#define FUS_ERR_BAD_DEGREE 100001
+#define FUS_ERR_BAD_ARGUMENT 100002
+
+/* flags for fus_stiffness* */
+#define FUS_TABLES_RESIDENT 1 /* dphi for this (P, type) already uploaded: skip the table copy */
+#define FUS_NO_ATOMICS 2      /* caller guarantees no two cells of this launch share a dof (colouring) */
+
+int fus_abi_version(void);
+const char* fus_last_error(void);
+/* Number of device kernels this library has launched since load / last reset
+ * (bench.py's `gpu_launches`). */
+int64_t fus_launch_count(void);
+void fus_reset_launch_count(void);
+
+/* --------------------------------------------------------------------- *
+ * Element operators
+ * --------------------------------------------------------------------- */
+
+/* Upload the 1-D derivative table dphi[q*n + i] = l_i'(x_q) for degree P to
+ * the constant bank the stiffness kernels read.  `dphi` may be a host or a
+ * device pointer.  Replaces the `dphi` kernel argument of
+ * cuda/operators.py:88-95 (read per thread from global at :138-151). */
+int fus_set_dphi_f64(int P, const double* dphi, void* stream);
+int fus_set_dphi_f32(int P, const float* dphi, void* stream);
+
+/* Stiffness action  y[dm[c,:]] += D^T-apply( coeff[c] * Gsym[c,q] * (D-apply x[dm[c,:]]) ).
+ * Replaces `stiffness_operator(P, float_type)[ncells, (n,n,n)](x, coeff, y, G, dofmap, dphi)`
+ * - cuda/operators.py:73-192 (CPU twin numba-cpu/operators.py:71-227,
+ * C++ cpp/common/spectral_op.hpp:173-243).
+ *   x, y   : (nd,)            y is accumulated into (caller zero-fills)
+ *   coeff  : (ncells,)
+ *   G      : (ncells, Nd, 6)  C order, [G00 G01 G02 G11 G12 G22] (cuda/precompute.py:158-163)
+ *   dofmap : (ncells, Nd)     int32, tensor-product order q = i*n*n + j*n + k
+ *   dphi   : (n, n)           device or host; ignored with FUS_TABLES_RESIDENT */
+int fus_stiffness_f64(const double* x, const double* coeff, double* y, const double* G,
+                      const int32_t* dofmap, const double* dphi, int64_t ncells, int P,
+                      int flags, void* stream);
+int fus_stiffness_f32(const float* x, const float* coeff, float* y, const float* G,
+                      const int32_t* dofmap, const float* dphi, int64_t ncells, int P,
+                      int flags, void* stream);
+
+/* Two stiffness actions sharing ONE read of G:
+ *   y += K(coeff_a ; xa) + K(coeff_b ; xb)
+ * Replaces the two back-to-back launches of the Westervelt stage,
+ * cuda/demo_nonlinear_bowl.py:620-625. */
+int fus_stiffness2_f64(const double* xa, const double* coeff_a, const double* xb,
+                       const double* coeff_b, double* y, const double* G,
+                       const int32_t* dofmap, const double* dphi, int64_t ncells, int P,
+                       int flags, void* stream);
+int fus_stiffness2_f32(const float* xa, const float* coeff_a, const float* xb,
+                       const float* coeff_b, float* y, const float* G, const int32_t* dofmap,
+                       const float* dphi, int64_t ncells, int P, int flags, void* stream);
+
+/* Mass (diagonal) action on cells or boundary facets
+ *   y[dm[e,i]] += x[dm[e,i]] * detJ[e,i] * coeff[e]
+ * Replaces `mass_operator[grid, block](x, coeff, y, detJ, dofmap)` -
+ * cuda/operators.py:18-70 (numba-cpu/operators.py:19-68,
+ * cpp/common/spectral_op.hpp:69-86).  ncols = Nd (cells) or n^2 (facets). */
+int fus_mass_f64(const double* x, const double* coeff, double* y, const double* detJ,
+                 const int32_t* dofmap, int64_t nent, int ncols, void* stream);
+int fus_mass_f32(const float* x, const float* coeff, float* y, const float* detJ,
+                 const int32_t* dofmap, int64_t nent, int ncols, void* stream);
+
+/* --------------------------------------------------------------------- *
+ * Vector kernels - cuda/operators.py:195-274
+ * --------------------------------------------------------------------- */
+int fus_axpy_f64(double alpha, const double* x, double* y, int64_t n, void* stream);
+int fus_axpy_f32(float alpha, const float* x, float* y, int64_t n, void* stream);
+int fus_copy_f64(const double* a, double* b, int64_t n, void* stream);
+int fus_copy_f32(const float* a, float* b, int64_t n, void* stream);
+int fus_fill_f64(double alpha, double* x, int64_t n, void* stream);
+int fus_fill_f32(float alpha, float* x, int64_t n, void* stream);
+int fus_pointwise_divide_f64(const double* a, const double* b, double* c, int64_t n, void* stream);
+int fus_pointwise_divide_f32(const float* a, const float* b, float* c, int64_t n, void* stream);
+int fus_square_f64(const double* a, double* b, int64_t n, void* stream);
+int fus_square_f32(const float* a, float* b, int64_t n, void* stream);
+
+/* --------------------------------------------------------------------- *
+ * Halo pack / unpack - cuda/scatterer.py:18-101.  N = size_local.
+ * --------------------------------------------------------------------- */
+int fus_pack_fwd_f64(const double* in, double* out, const int64_t* index, int64_t n, void* stream);
+int fus_pack_fwd_f32(const float* in, float* out, const int64_t* index, int64_t n, void* stream);
+int fus_unpack_fwd_f64(const double* in, double* out, const int64_t* index, int64_t n, int64_t N, void* stream);
+int fus_unpack_fwd_f32(const float* in, float* out, const int64_t* index, int64_t n, int64_t N, void* stream);
+int fus_pack_rev_f64(const double* in, double* out, const int64_t* index, int64_t n, int64_t N, void* stream);
+int fus_pack_rev_f32(const float* in, float* out, const int64_t* index, int64_t n, int64_t N, void* stream);
+int fus_unpack_rev_f64(const double* in, double* out, const int64_t* index, int64_t n, void* stream);
+int fus_unpack_rev_f32(const float* in, float* out, const int64_t* index, int64_t n, void* stream);
+/* k vectors through one index list in one launch (the 2-3 forward scatters
+ * of one RK stage, cuda/demo_linear_box.py:537-538, demo_nonlinear_bowl.py:604-606):
+ *   out[v*n + i] = in_v[index[i] (+N)]   /   in_v[index[i] (+N)] (+)= in[v*n + i] */
+int fus_pack_multi_f64(const double* const* in, int nvec, double* out, const int64_t* index,
+                       int64_t n, int64_t offset, void* stream);
+int fus_pack_multi_f32(const float* const* in, int nvec, float* out, const int64_t* index,
+                       int64_t n, int64_t offset, void* stream);
+int fus_unpack_multi_f64(const double* in, double* const* out, int nvec, const int64_t* index,
+                         int64_t n, int64_t offset, int add, void* stream);
+int fus_unpack_multi_f32(const float* in, float* const* out, int nvec, const int64_t* index,
+                         int64_t n, int64_t offset, int add, void* stream);
+
+/* --------------------------------------------------------------------- *
+ * Fused RK4 stage kernels.  Replace the 13 vector launches per stage of
+ * cuda/demo_linear_box.py:491-563 (numba-cpu/demo_linear_box.py:425-459,
+ * cpp/common/Linear.hpp:237-344).
+ * --------------------------------------------------------------------- */
+
+/* Stage opening (first stage of a step, or any stage when not chained):
+ *   [first != 0: u0 = u; v0 = v]
+ *   un = u0 + adt*ku ; vn = v0 + adt*kv ; ku = vn ; b = 0
+ * (copy/axpy/copy/fill of :491-508, :541).  `vn` is stored in ku (f0: ku = vn). */
+int fus_rk_open_f64(const double* u, const double* v, double* u0, double* v0, double* ku,
+                    const double* kv, double* un, double* b, double adt, int first, int64_t n,
+                    void* stream);
+int fus_rk_open_f32(const float* u, const float* v, float* u0, float* v0, float* ku,
+                    const float* kv, float* un, float* b, float adt, int first, int64_t n,
+                    void* stream);
+
+/* Stage closing, optionally chained with the next stage's opening:
+ *   kv = b / m ; u += bdt*ku ; v += bdt*kv                       (:556-563)
+ *   next_mode 1: un = u0 + adt_next*ku ; ku' = v0 + adt_next*kv ; b = 0
+ *   next_mode 2: (step boundary) u0 = u ; v0 = v ; un = u ; ku' = v ; b = 0
+ *   next_mode 0: nothing more (kv is stored)
+ * In modes 1 and 2 kv is still stored so a later un-chained stage can read it. */
+int fus_rk_close_f64(double* u, double* v, double* u0, double* v0, double* ku, double* kv,
+                     double* un, double* b, const double* m, double bdt, double adt_next,
+                     int next_mode, int64_t n, void* stream);
+int fus_rk_close_f32(float* u, float* v, float* u0, float* v0, float* ku, float* kv, float* un,
+                     float* b, const float* m, float bdt, float adt_next, int next_mode,
+                     int64_t n, void* stream);
+
+/* Boundary-facet terms of one stage through precomputed diagonals on a compact
+ * dof list: b[dof[i]] += g * src[i] + dg * src2[i] + vn[dof[i]] * absb[i].
+ * Replaces the facet `mass_operator` launches of :546-551 (and
+ * demo_nonlinear_bowl.py:629-639); src/src2/absb are those operators applied
+ * to a vector of ones once at start-up.  Any of src, src2, absb may be NULL. */
+int fus_boundary_terms_f64(double* b, const double* vn, const int32_t* dof, const double* src,
+                           const double* src2, const double* absb, double g, double dg,
+                           int64_t n, void* stream);
+int fus_boundary_terms_f32(float* b, const float* vn, const int32_t* dof, const float* src,
+                           const float* src2, const float* absb, float g, float dg, int64_t n,
+                           void* stream);
+
+/* Westervelt stage helpers (cuda/demo_nonlinear_bowl.py:603-650):
+ *   w = vn*vn                                                   (:603)
+ *   fused cell-mass pair sharing one read of detJ and the dofmap:
+ *     m[dm] += c2 * detJ * un[dm]       (state-dependent LHS, :610-612)
+ *     b[dm] += c5 * detJ * vn[dm]^2     (:626-628)
+ *   m += m0 is folded into the closing kernel below. */
+int fus_westervelt_mass_f64(const double* un, const double* vn, const double* c2,
+                            const double* c5, double* m, double* b, const double* detJ,
+                            const int32_t* dofmap, int64_t ncells, int ncols, void* stream);
+int fus_westervelt_mass_f32(const float* un, const float* vn, const float* c2, const float* c5,
+                            float* m, float* b, const float* detJ, const int32_t* dofmap,
+                            int64_t ncells, int ncols, void* stream);
+/* kv = b / (m + m0); u += bdt*ku; v += bdt*kv; then as fus_rk_close (also zeroes m). */
+int fus_rk_close_westervelt_f64(double* u, double* v, double* u0, double* v0, double* ku,
+                                double* kv, double* un, double* b, double* m, const double* m0,
+                                double bdt, double adt_next, int next_mode, int64_t n,
+                                void* stream);
+int fus_rk_close_westervelt_f32(float* u, float* v, float* u0, float* v0, float* ku, float* kv,
+                                float* un, float* b, float* m, const float* m0, float bdt,
+                                float adt_next, int next_mode, int64_t n, void* stream);
+
+/* --------------------------------------------------------------------- *
+ * Geometry precompute on the device - cuda/precompute.py:17-163
+ * (cpp/common/precompute.hpp:33-213).
+ *   x_dofs (ncells, 8) int32; x_g (nv, 3); dphi (3, nq, 8); w (nq,)
+ *   G (ncells, nq, 6); detJ (ncells, nq); either output may be NULL.
+ * --------------------------------------------------------------------- */
+int fus_geometry_f64(double* G, double* detJ, const int32_t* x_dofs, const double* x_g,
+                     const double* dphi, const double* w, int64_t ncells, int nq, void* stream);
+int fus_geometry_f32(float* G, float* detJ, const int32_t* x_dofs, const float* x_g,
+                     const float* dphi, const float* w, int64_t ncells, int nq, void* stream);
+/* boundary_data (nf, 2) int32 = (cell, local facet); dphi_f (6, 3, nq_f, 8) */
+int fus_facet_geometry_f64(double* detJ_f, const int32_t* x_dofs, const double* x_g,
+                           const int32_t* boundary_data, const double* dphi_f, const double* w,
+                           int64_t nf, int nq_f, void* stream);
+int fus_facet_geometry_f32(float* detJ_f, const int32_t* x_dofs, const float* x_g,
+                           const int32_t* boundary_data, const float* dphi_f, const float* w,
+                           int64_t nf, int nq_f, void* stream);
+
+/* --------------------------------------------------------------------- *
+ * Host-buffer entry points (the end-to-end path: host <-> device copies are
+ * inside the call).  x_host / y_host are HOST pointers (pinned for full
+ * speed); every other pointer is a device pointer as above.
+ * y_host += K x_host, staged through the caller-provided device scratch
+ * x_dev / y_dev (nd each).  Synchronous on return.
+ * --------------------------------------------------------------------- */
+int fus_stiffness_host_f64(const double* x_host, double* y_host, int64_t nd, double* x_dev,
+                           double* y_dev, const double* coeff, const double* G,
+                           const int32_t* dofmap, const double* dphi, int64_t ncells, int P,
+                           int flags, void* stream);
+int fus_stiffness_host_f32(const float* x_host, float* y_host, int64_t nd, float* x_dev,
+                           float* y_dev, const float* coeff, const float* G,
+                           const int32_t* dofmap, const float* dphi, int64_t ncells, int P,
+                           int flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUS_B200_H */
