@@ -1,0 +1,315 @@
+// Fused RK4 stage kernels, sm_100a.
+//
+// The reference runs one RK stage as 13 separate vector launches plus two
+// facet mass launches (/root/reference/cuda/demo_linear_box.py:491-563;
+// CPU twin numba-cpu/demo_linear_box.py:425-459; C++ cpp/common/Linear.hpp:
+// 237-344), every one a full pass over 2-3 vectors.  Here a stage is
+//     [open]  ->  stiffness (+ boundary terms)  ->  close (chained with the
+//                                                    next stage's open)
+// so the vector work of a stage is ONE pass: 7 reads + 5 writes per dof.
+//
+// Stage algebra (a, b = Butcher coefficients; ku holds vn, "f0: ku = vn"):
+//   open : un = u0 + a dt ku ; vn = v0 + a dt kv ; ku <- vn ; b <- 0
+//   close: kv = b / m ; u += b_i dt ku ; v += b_i dt kv
+// Pure HBM streams, 16-byte vector accesses, grid-stride over a few waves.
+
+#include <initializer_list>
+
+#include "fus_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <typename T>
+struct Vec;
+template <>
+struct Vec<double> {
+  using type = double2;
+  static constexpr int W = 2;
+};
+template <>
+struct Vec<float> {
+  using type = float4;
+  static constexpr int W = 4;
+};
+
+template <typename T, int W>
+struct Pack {
+  T v[W];
+};
+
+template <typename T, bool VEC>
+__device__ __forceinline__ Pack<T, Vec<T>::W> ld(const T* p, long long k) {
+  Pack<T, Vec<T>::W> r;
+  if constexpr (VEC) {
+    *reinterpret_cast<typename Vec<T>::type*>(r.v) =
+        reinterpret_cast<const typename Vec<T>::type*>(p)[k];
+  } else {
+    r.v[0] = p[k];
+  }
+  return r;
+}
+template <typename T, bool VEC>
+__device__ __forceinline__ void st(T* p, long long k, const Pack<T, Vec<T>::W>& r) {
+  if constexpr (VEC) {
+    reinterpret_cast<typename Vec<T>::type*>(p)[k] =
+        *reinterpret_cast<const typename Vec<T>::type*>(r.v);
+  } else {
+    p[k] = r.v[0];
+  }
+}
+
+template <typename T>
+struct OpenArgs {
+  const T* u;
+  const T* v;
+  T* u0;
+  T* v0;
+  T* ku;
+  const T* kv;
+  T* un;
+  T* b;
+  T adt;
+  int first;
+  long long n;
+};
+
+template <typename T, bool VEC>
+__device__ __forceinline__ void open_body(const OpenArgs<T>& a, long long k) {
+  constexpr int W = VEC ? Vec<T>::W : 1;
+  using P = Pack<T, Vec<T>::W>;
+  P u0, v0, ku, kv, un, vn, z;
+  if (a.first) {
+    u0 = ld<T, VEC>(a.u, k);
+    v0 = ld<T, VEC>(a.v, k);
+    st<T, VEC>(a.u0, k, u0);
+    st<T, VEC>(a.v0, k, v0);
+  } else {
+    u0 = ld<T, VEC>(a.u0, k);
+    v0 = ld<T, VEC>(a.v0, k);
+  }
+  ku = ld<T, VEC>(a.ku, k);
+  kv = ld<T, VEC>(a.kv, k);
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    un.v[w] = a.adt * ku.v[w] + u0.v[w];
+    vn.v[w] = a.adt * kv.v[w] + v0.v[w];
+    z.v[w] = T(0);
+  }
+  st<T, VEC>(a.un, k, un);
+  st<T, VEC>(a.ku, k, vn);
+  st<T, VEC>(a.b, k, z);
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kThreads) rk_open_kernel(const OpenArgs<T> a) {
+  constexpr int W = VEC ? Vec<T>::W : 1;
+  const long long stride = (long long)gridDim.x * kThreads;
+  const long long i0 = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const long long nv = a.n / W;
+  for (long long k = i0; k < nv; k += stride) open_body<T, VEC>(a, k);
+  if constexpr (VEC) {
+    const long long k = nv * W + i0;
+    if (k < a.n) open_body<T, false>(a, k);
+  }
+}
+
+template <typename T>
+struct CloseArgs {
+  T* u;
+  T* v;
+  T* u0;
+  T* v0;
+  T* ku;
+  T* kv;  // may be null when chained (next_mode != 0)
+  T* un;
+  T* b;
+  T* m;         // Westervelt: state-dependent part, zeroed here; linear: the lumped mass (read only)
+  const T* m0;  // Westervelt only
+  T bdt;
+  T adt_next;
+  int next_mode;
+  long long n;
+  long long* step;  // device step counter, incremented at a step boundary (may be null)
+};
+
+template <typename T, bool VEC, bool WEST>
+__device__ __forceinline__ void close_body(const CloseArgs<T>& a, long long k) {
+  constexpr int W = VEC ? Vec<T>::W : 1;
+  using P = Pack<T, Vec<T>::W>;
+  P b = ld<T, VEC>(a.b, k);
+  P m = ld<T, VEC>(a.m, k);
+  P ku = ld<T, VEC>(a.ku, k);
+  P u = ld<T, VEC>(a.u, k);
+  P v = ld<T, VEC>(a.v, k);
+  P kv, z;
+  if constexpr (WEST) {
+    P m0 = ld<T, VEC>(a.m0, k);
+#pragma unroll
+    for (int w = 0; w < W; ++w) m.v[w] = m.v[w] + m0.v[w];  // axpy(1.0, m0, m)
+  }
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    kv.v[w] = b.v[w] / m.v[w];
+    u.v[w] = a.bdt * ku.v[w] + u.v[w];
+    v.v[w] = a.bdt * kv.v[w] + v.v[w];
+    z.v[w] = T(0);
+  }
+  st<T, VEC>(a.u, k, u);
+  st<T, VEC>(a.v, k, v);
+  if (a.kv != nullptr) st<T, VEC>(a.kv, k, kv);
+  if constexpr (WEST) st<T, VEC>(a.m, k, z);
+  if (a.next_mode == 1) {
+    P u0 = ld<T, VEC>(a.u0, k);
+    P v0 = ld<T, VEC>(a.v0, k);
+    P un, vn;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      un.v[w] = a.adt_next * ku.v[w] + u0.v[w];
+      vn.v[w] = a.adt_next * kv.v[w] + v0.v[w];
+    }
+    st<T, VEC>(a.un, k, un);
+    st<T, VEC>(a.ku, k, vn);
+    st<T, VEC>(a.b, k, z);
+  } else if (a.next_mode == 2) {
+    st<T, VEC>(a.u0, k, u);
+    st<T, VEC>(a.v0, k, v);
+    st<T, VEC>(a.un, k, u);
+    st<T, VEC>(a.ku, k, v);
+    st<T, VEC>(a.b, k, z);
+  }
+}
+
+template <typename T, bool VEC, bool WEST>
+__global__ void __launch_bounds__(kThreads) rk_close_kernel(const CloseArgs<T> a) {
+  constexpr int W = VEC ? Vec<T>::W : 1;
+  const long long stride = (long long)gridDim.x * kThreads;
+  const long long i0 = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const long long nv = a.n / W;
+  for (long long k = i0; k < nv; k += stride) close_body<T, VEC, WEST>(a, k);
+  if constexpr (VEC) {
+    const long long k = nv * W + i0;
+    if (k < a.n) close_body<T, false, WEST>(a, k);
+  }
+  if (a.step != nullptr && a.next_mode == 2 && i0 == 0) *a.step += 1;
+}
+
+// b[dof[i]] += g*src[i] + dg*src2[i] + vn[dof[i]]*absb[i]; the dof list is unique
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    boundary_kernel(T* b, const T* __restrict__ vn, const int32_t* __restrict__ dof,
+                    const T* __restrict__ src, const T* __restrict__ src2,
+                    const T* __restrict__ absb, T g, T dg, const T* __restrict__ gtab,
+                    const long long* __restrict__ step, int gstride, int goff, long long n) {
+  if (gtab != nullptr) {
+    const long long s = step != nullptr ? *step : 0;
+    g = gtab[s * gstride + goff];
+    dg = gtab[s * gstride + goff + 1];
+  }
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const int d = dof[i];
+    T acc = T(0);
+    if (src != nullptr) acc += g * src[i];
+    if (src2 != nullptr) acc += dg * src2[i];
+    if (absb != nullptr) acc += vn[d] * absb[i];
+    b[d] += acc;
+  }
+}
+
+inline unsigned grid_for(long long n) {
+  long long blocks = (n + kThreads - 1) / kThreads;
+  const long long cap = (long long)fus_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+
+inline bool aligned16(std::initializer_list<const void*> ps) {
+  uintptr_t bits = 0;
+  for (const void* p : ps) bits |= reinterpret_cast<uintptr_t>(p);
+  return (bits & 15u) == 0;
+}
+
+template <typename T>
+int open_entry(const T* u, const T* v, T* u0, T* v0, T* ku, const T* kv, T* un, T* b, T adt,
+               int first, int64_t n, void* stream) {
+  if (n < 0) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_open: n < 0");
+  if (n == 0) return 0;
+  OpenArgs<T> a{u, v, u0, v0, ku, kv, un, b, adt, first, n};
+  cudaStream_t st_ = static_cast<cudaStream_t>(stream);
+  if (aligned16({u, v, u0, v0, ku, kv, un, b})) {
+    rk_open_kernel<T, true><<<grid_for(n / Vec<T>::W + 1), kThreads, 0, st_>>>(a);
+  } else {
+    rk_open_kernel<T, false><<<grid_for(n), kThreads, 0, st_>>>(a);
+  }
+  FUS_LAUNCH_CHECK("rk_open_kernel");
+  return 0;
+}
+
+template <typename T, bool WEST>
+int close_entry(T* u, T* v, T* u0, T* v0, T* ku, T* kv, T* un, T* b, T* m, const T* m0, T bdt,
+                T adt_next, int next_mode, int64_t n, int64_t* step, void* stream) {
+  if (n < 0) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close: n < 0");
+  if (next_mode < 0 || next_mode > 2) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close: next_mode");
+  if (next_mode == 0 && kv == nullptr)
+    return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close: kv must be stored when not chained");
+  if (n == 0) return 0;
+  CloseArgs<T> a{u, v, u0, v0, ku, kv, un, b, m, m0, bdt, adt_next, next_mode, n,
+                 reinterpret_cast<long long*>(step)};
+  cudaStream_t st_ = static_cast<cudaStream_t>(stream);
+  if (aligned16({u, v, u0, v0, ku, kv, un, b, m, m0})) {
+    rk_close_kernel<T, true, WEST><<<grid_for(n / Vec<T>::W + 1), kThreads, 0, st_>>>(a);
+  } else {
+    rk_close_kernel<T, false, WEST><<<grid_for(n), kThreads, 0, st_>>>(a);
+  }
+  FUS_LAUNCH_CHECK("rk_close_kernel");
+  return 0;
+}
+
+template <typename T>
+int boundary_entry(T* b, const T* vn, const int32_t* dof, const T* src, const T* src2,
+                   const T* absb, T g, T dg, const T* gtab, const int64_t* step, int gstride,
+                   int goff, int64_t n, void* stream) {
+  if (n < 0) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "boundary_terms: n < 0");
+  if (n == 0) return 0;
+  boundary_kernel<T><<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      b, vn, dof, src, src2, absb, g, dg, gtab, reinterpret_cast<const long long*>(step), gstride,
+      goff, n);
+  FUS_LAUNCH_CHECK("boundary_kernel");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+#define FUS_RK_API(SFX, T)                                                                       \
+  int fus_rk_open_##SFX(const T* u, const T* v, T* u0, T* v0, T* ku, const T* kv, T* un, T* b,   \
+                        T adt, int first, int64_t n, void* s) {                                  \
+    return open_entry<T>(u, v, u0, v0, ku, kv, un, b, adt, first, n, s);                         \
+  }                                                                                              \
+  int fus_rk_close_##SFX(T* u, T* v, T* u0, T* v0, T* ku, T* kv, T* un, T* b, const T* m, T bdt, \
+                         T adt_next, int next_mode, int64_t n, int64_t* step_dev, void* s) {     \
+    return close_entry<T, false>(u, v, u0, v0, ku, kv, un, b, const_cast<T*>(m), nullptr, bdt,   \
+                                 adt_next, next_mode, n, step_dev, s);                           \
+  }                                                                                              \
+  int fus_rk_close_westervelt_##SFX(T* u, T* v, T* u0, T* v0, T* ku, T* kv, T* un, T* b, T* m,   \
+                                    const T* m0, T bdt, T adt_next, int next_mode, int64_t n,    \
+                                    int64_t* step_dev, void* s) {                                \
+    return close_entry<T, true>(u, v, u0, v0, ku, kv, un, b, m, m0, bdt, adt_next, next_mode, n, \
+                                step_dev, s);                                                    \
+  }                                                                                              \
+  int fus_boundary_terms_##SFX(T* b, const T* vn, const int32_t* dof, const T* src,              \
+                               const T* src2, const T* absb, T g, T dg, const T* gtab,           \
+                               const int64_t* step_dev, int gstride, int goff, int64_t n,        \
+                               void* s) {                                                        \
+    return boundary_entry<T>(b, vn, dof, src, src2, absb, g, dg, gtab, step_dev, gstride, goff,  \
+                             n, s);                                                              \
+  }
+
+FUS_RK_API(f64, double)
+FUS_RK_API(f32, float)
+#undef FUS_RK_API
+
+}  // extern "C"

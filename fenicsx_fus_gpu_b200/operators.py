@@ -1,0 +1,155 @@
+"""
+Operators - the reference's device-kernel surface on hand-written sm_100a CUDA
+==============================================================================
+
+Drop-in for ``/root/reference/cuda/operators.py``: same names, same argument
+order, same accumulate-into-``y`` semantics, same ``kernel[grid, block](*args)``
+launch syntax (the ``[grid, block]`` hint is accepted and ignored - the native
+kernels size themselves to the 148 SMs).
+
+    mass_operator[nb, 128](x, entity_constants, y, detJ_entity, entity_dofmap)     # :18-70
+    stiffness_operator(P, float_type)[ncells, (n, n, n)](x, c, y, G, dofmap, dphi)  # :73-192
+    axpy[nb, 1024](alpha, x, y); copy[..](a, b); fill[..](alpha, x)                 # :195-241
+    pointwise_divide[..](a, b, c); square[..](a, b)                                 # :244-274
+
+Array arguments are device arrays: anything exposing
+``__cuda_array_interface__`` (torch CUDA tensors, Numba ``DeviceNDArray`` -
+what the reference's call sites pass).  Launches are asynchronous on torch's
+current stream.  There is no CPU path: host arrays raise.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, current_stream, dev, fn
+
+FUS_TABLES_RESIDENT = 1
+FUS_NO_ATOMICS = 2
+
+
+class _Kernel:
+    """``kernel[grid, block](*args)`` launch syntax of Numba CUDA kernels."""
+
+    def __getitem__(self, _launch_config):
+        return self
+
+    def __call__(self, *args):  # pragma: no cover - abstract
+        raise NotImplementedError
+
+
+class _Mass(_Kernel):
+    """``y[dm[e,i]] += x[dm[e,i]] * detJ[e,i] * c[e]`` - cuda/operators.py:18-70."""
+
+    def __call__(self, x, entity_constants, y, detJ_entity, entity_dofmap):
+        xd = dev(x)
+        T = xd.dtype
+        yd, cd, jd = dev(y, T), dev(entity_constants, T), dev(detJ_entity, T)
+        dm = dev(entity_dofmap, np.int32)
+        if len(dm.shape) != 2 or jd.shape != dm.shape:
+            raise _lib.FusError(f"mass_operator: dofmap {dm.shape} / detJ {jd.shape} shape mismatch")
+        if cd.size != dm.shape[0]:
+            raise _lib.FusError("mass_operator: one constant per entity expected")
+        if dm.shape[0] == 0:
+            # Numba refuses a zero-size grid (the reference guards with `if bfacet_dofmap.any()`)
+            raise ValueError("mass_operator: zero entities (empty launch)")
+        check(fn("fus_mass", T)(xd.ptr, cd.ptr, yd.ptr, jd.ptr, dm.ptr, dm.shape[0], dm.shape[1],
+                                current_stream()), "fus_mass")
+
+
+mass_operator = _Mass()
+
+
+class _Stiffness(_Kernel):
+    """Sum-factorised stiffness action - cuda/operators.py:87-190."""
+
+    def __init__(self, P: int, float_type):
+        if not 2 <= int(P) <= 7:
+            raise ValueError(f"stiffness_operator: degree {P} not in 2..7")
+        self.P = int(P)
+        self.n = self.P + 1
+        self.float_type = np.dtype(float_type)
+        _lib.sfx(self.float_type)  # validates
+        self.flags = 0
+
+    def __call__(self, x, entity_constants, y, G_entity, entity_dofmap, dphi):
+        T = self.float_type
+        xd, yd, cd, gd = dev(x, T), dev(y, T), dev(entity_constants, T), dev(G_entity, T)
+        dm = dev(entity_dofmap, np.int32)
+        nd3 = self.n**3
+        if len(dm.shape) != 2 or dm.shape[1] != nd3:
+            raise _lib.FusError(f"stiffness_operator: dofmap must be (ncells, {nd3}), got {dm.shape}")
+        if gd.size != dm.shape[0] * nd3 * 6:
+            raise _lib.FusError("stiffness_operator: G must be (ncells, n^3, 6)")
+        if cd.size != dm.shape[0]:
+            raise _lib.FusError("stiffness_operator: one constant per cell expected")
+        if dm.shape[0] == 0:
+            raise ValueError("stiffness_operator: zero cells (empty launch)")
+        if isinstance(dphi, np.ndarray):  # host table is fine: it goes to the constant bank
+            tab = np.ascontiguousarray(dphi, dtype=T)
+            if tab.size != self.n**2:
+                raise _lib.FusError("stiffness_operator: dphi must be (n, n)")
+            ptr = tab.ctypes.data
+        else:
+            td = dev(dphi, T)
+            if td.size != self.n**2:
+                raise _lib.FusError("stiffness_operator: dphi must be (n, n)")
+            ptr = td.ptr
+        check(fn("fus_stiffness", T)(xd.ptr, cd.ptr, yd.ptr, gd.ptr, dm.ptr, ptr, dm.shape[0],
+                                     self.P, self.flags, current_stream()), "fus_stiffness")
+
+
+def stiffness_operator(P, float_type):
+    """Returns the stiffness kernel for degree ``P`` and ``float_type``
+    (cuda/operators.py:73-192)."""
+    return _Stiffness(P, float_type)
+
+
+def _vec3(name):
+    class K(_Kernel):
+        def __call__(self, a, b, c):
+            ad = dev(a)
+            T = ad.dtype
+            bd, cd_ = dev(b, T), dev(c, T)
+            n = min(ad.size, bd.size, cd_.size)
+            check(fn(name, T)(ad.ptr, bd.ptr, cd_.ptr, n, current_stream()), name)
+
+    return K()
+
+
+def _vec2(name):
+    class K(_Kernel):
+        def __call__(self, a, b):
+            ad = dev(a)
+            T = ad.dtype
+            bd = dev(b, T)
+            check(fn(name, T)(ad.ptr, bd.ptr, min(ad.size, bd.size), current_stream()), name)
+
+    return K()
+
+
+class _Axpy(_Kernel):
+    """``y = alpha*x + y`` - cuda/operators.py:195-209."""
+
+    def __call__(self, alpha, x, y):
+        xd = dev(x)
+        T = xd.dtype
+        yd = dev(y, T)
+        check(fn("fus_axpy", T)(float(alpha), xd.ptr, yd.ptr, min(xd.size, yd.size),
+                                current_stream()), "fus_axpy")
+
+
+class _Fill(_Kernel):
+    """``x[:] = alpha`` - cuda/operators.py:228-241."""
+
+    def __call__(self, alpha, x):
+        xd = dev(x)
+        check(fn("fus_fill", xd.dtype)(float(alpha), xd.ptr, xd.size, current_stream()), "fus_fill")
+
+
+axpy = _Axpy()
+fill = _Fill()
+copy = _vec2("fus_copy")  # b = a            cuda/operators.py:212-225
+square = _vec2("fus_square")  # b = a*a      cuda/operators.py:261-274
+pointwise_divide = _vec3("fus_pointwise_divide")  # c = a/b   cuda/operators.py:244-258

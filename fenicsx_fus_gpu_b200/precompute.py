@@ -1,0 +1,123 @@
+"""
+Precompute - geometry tables, computed on the GPU
+=================================================
+
+Drop-in for ``/root/reference/cuda/precompute.py`` (== ``numba-cpu/precompute.py``;
+C++ ``cpp/common/precompute.hpp:33-213``): same three functions, same argument
+order, each fills a caller-allocated output in place.
+
+The reference evaluates these with serial Numba loops on the host (64 M
+quadrature points at the 33 M-dof box, 2e9 at 1 B dofs).  Here one sm_100a
+thread handles one (entity, quadrature point) (``csrc/geometry.cu``).  Outputs
+and inputs may be device arrays (used in place) or host numpy arrays (staged
+through the device: the arithmetic always runs on the GPU, there is no CPU
+path).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, current_stream, fn
+
+
+def _to_dev(a, dtype):
+    """Device tensor for ``a`` (numpy -> upload; device array -> as is)."""
+    import torch
+
+    if isinstance(a, np.ndarray):
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).cuda(), True
+    if isinstance(a, torch.Tensor):
+        return a, False
+    d = _lib.dev(a)  # __cuda_array_interface__ object
+    if d.dtype != np.dtype(dtype):
+        raise _lib.FusError(f"expected dtype {np.dtype(dtype)}, got {d.dtype}")
+    return a, False
+
+
+def _ptr(a):
+    return _lib.dev(a).ptr
+
+
+def _out(a):
+    """(device buffer, host array to copy back into or None)"""
+    import torch
+
+    if isinstance(a, np.ndarray):
+        tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32}[a.dtype]
+        return torch.empty(a.shape, dtype=tdt, device="cuda"), a
+    return a, None
+
+
+def _finish(buf, host):
+    if host is not None:
+        host[...] = buf.cpu().numpy()
+
+
+def compute_scaled_jacobian_determinant(detJ, mesh, num_cell, dphi, weights):
+    """``detJ[c, q] = w_q |det J_c(x_q)|`` - cuda/precompute.py:76-112."""
+    x_dofs, x_g = mesh
+    buf, host = _out(detJ)
+    T = _lib.dev(buf).dtype
+    xd, _ = _to_dev(x_dofs, np.int32)
+    xg, _ = _to_dev(x_g, T)
+    dp, _ = _to_dev(dphi, T)
+    w, _ = _to_dev(weights, T)
+    nq = int(_lib.dev(w).size)
+    check(fn("fus_geometry", T)(None, _ptr(buf), _ptr(xd), _ptr(xg), _ptr(dp), _ptr(w),
+                                int(num_cell), nq, current_stream()), "fus_geometry")
+    _finish(buf, host)
+
+
+def compute_scaled_geometrical_factor(G, mesh, num_cell, dphi, weights):
+    """``G[c, q, :] = w_q |det J| (J^-1 J^-T)`` upper triangle
+    ``[00, 01, 02, 11, 12, 22]`` - cuda/precompute.py:115-163."""
+    x_dofs, x_g = mesh
+    buf, host = _out(G)
+    T = _lib.dev(buf).dtype
+    xd, _ = _to_dev(x_dofs, np.int32)
+    xg, _ = _to_dev(x_g, T)
+    dp, _ = _to_dev(dphi, T)
+    w, _ = _to_dev(weights, T)
+    nq = int(_lib.dev(w).size)
+    check(fn("fus_geometry", T)(_ptr(buf), None, _ptr(xd), _ptr(xg), _ptr(dp), _ptr(w),
+                                int(num_cell), nq, current_stream()), "fus_geometry")
+    _finish(buf, host)
+
+
+def compute_geometry(G, detJ, mesh, num_cell, dphi, weights):
+    """Both tables in one pass over the cells (not in the reference, which
+    makes two passes: cuda/demo_linear_box.py:245-253)."""
+    x_dofs, x_g = mesh
+    gbuf, ghost = _out(G)
+    jbuf, jhost = _out(detJ)
+    T = _lib.dev(gbuf).dtype
+    xd, _ = _to_dev(x_dofs, np.int32)
+    xg, _ = _to_dev(x_g, T)
+    dp, _ = _to_dev(dphi, T)
+    w, _ = _to_dev(weights, T)
+    nq = int(_lib.dev(w).size)
+    check(fn("fus_geometry", T)(_ptr(gbuf), _ptr(jbuf), _ptr(xd), _ptr(xg), _ptr(dp), _ptr(w),
+                                int(num_cell), nq, current_stream()), "fus_geometry")
+    _finish(gbuf, ghost)
+    _finish(jbuf, jhost)
+
+
+def compute_boundary_facets_scaled_jacobian_determinant(detJ_f, mesh, boundary_data, dphi_f, weights):
+    """``detJ_f[i, q] = w_q |J_facet|`` for ``boundary_data[i] = (cell, local
+    facet)`` - cuda/precompute.py:17-73."""
+    x_dofs, x_g = mesh
+    buf, host = _out(detJ_f)
+    T = _lib.dev(buf).dtype
+    xd, _ = _to_dev(x_dofs, np.int32)
+    xg, _ = _to_dev(x_g, T)
+    bd, _ = _to_dev(boundary_data, np.int32)
+    dp, _ = _to_dev(dphi_f, T)
+    w, _ = _to_dev(weights, T)
+    nq = int(_lib.dev(w).size)
+    nf = int(_lib.dev(bd).shape[0])
+    if nf:
+        check(fn("fus_facet_geometry", T)(_ptr(buf), _ptr(xd), _ptr(xg), _ptr(bd), _ptr(dp), _ptr(w),
+                                          nf, nq, current_stream()), "fus_facet_geometry")
+    _finish(buf, host)

@@ -123,7 +123,10 @@ int fus_unpack_rev_f64(const double* in, double* out, const int64_t* index, int6
 int fus_unpack_rev_f32(const float* in, float* out, const int64_t* index, int64_t n, void* stream);
 /* k vectors through one index list in one launch (the 2-3 forward scatters
  * of one RK stage, cuda/demo_linear_box.py:537-538, demo_nonlinear_bowl.py:604-606):
- *   out[v*n + i] = in_v[index[i] (+N)]   /   in_v[index[i] (+N)] (+)= in[v*n + i] */
+ *   out[i*nvec + v] = in_v[index[i] + offset]   /   out_v[index[i] + offset] (+)= in[i*nvec + v]
+ * The buffer is entry-major so that a contiguous range of entries (one
+ * neighbour's segment of a concatenated index list) carries all vectors:
+ * ONE pack launch serves every neighbour. */
 int fus_pack_multi_f64(const double* const* in, int nvec, double* out, const int64_t* index,
                        int64_t n, int64_t offset, void* stream);
 int fus_pack_multi_f32(const float* const* in, int nvec, float* out, const int64_t* index,
@@ -154,26 +157,34 @@ int fus_rk_open_f32(const float* u, const float* v, float* u0, float* v0, float*
  *   kv = b / m ; u += bdt*ku ; v += bdt*kv                       (:556-563)
  *   next_mode 1: un = u0 + adt_next*ku ; ku' = v0 + adt_next*kv ; b = 0
  *   next_mode 2: (step boundary) u0 = u ; v0 = v ; un = u ; ku' = v ; b = 0
- *   next_mode 0: nothing more (kv is stored)
- * In modes 1 and 2 kv is still stored so a later un-chained stage can read it. */
+ *   next_mode 0: nothing more
+ * kv is stored when non-NULL; it may be NULL in modes 1 and 2 (nothing reads
+ * it again).  step_dev (may be NULL) is a device step counter incremented in
+ * mode 2 - it indexes the source table of fus_boundary_terms, so a whole RK
+ * step can be replayed as a CUDA graph with no host work. */
 int fus_rk_close_f64(double* u, double* v, double* u0, double* v0, double* ku, double* kv,
                      double* un, double* b, const double* m, double bdt, double adt_next,
-                     int next_mode, int64_t n, void* stream);
+                     int next_mode, int64_t n, int64_t* step_dev, void* stream);
 int fus_rk_close_f32(float* u, float* v, float* u0, float* v0, float* ku, float* kv, float* un,
                      float* b, const float* m, float bdt, float adt_next, int next_mode,
-                     int64_t n, void* stream);
+                     int64_t n, int64_t* step_dev, void* stream);
 
 /* Boundary-facet terms of one stage through precomputed diagonals on a compact
- * dof list: b[dof[i]] += g * src[i] + dg * src2[i] + vn[dof[i]] * absb[i].
+ * list of UNIQUE dofs: b[dof[i]] += g * src[i] + dg * src2[i] + vn[dof[i]] * absb[i].
  * Replaces the facet `mass_operator` launches of :546-551 (and
  * demo_nonlinear_bowl.py:629-639); src/src2/absb are those operators applied
- * to a vector of ones once at start-up.  Any of src, src2, absb may be NULL. */
+ * to a vector of ones once at start-up.  Any of src, src2, absb may be NULL.
+ * Source amplitudes: the scalars g, dg, or - when gtab != NULL - the device
+ * table entries gtab[step*gstride + goff], gtab[step*gstride + goff + 1] with
+ * step = *step_dev (0 when step_dev is NULL). */
 int fus_boundary_terms_f64(double* b, const double* vn, const int32_t* dof, const double* src,
                            const double* src2, const double* absb, double g, double dg,
+                           const double* gtab, const int64_t* step_dev, int gstride, int goff,
                            int64_t n, void* stream);
 int fus_boundary_terms_f32(float* b, const float* vn, const int32_t* dof, const float* src,
-                           const float* src2, const float* absb, float g, float dg, int64_t n,
-                           void* stream);
+                           const float* src2, const float* absb, float g, float dg,
+                           const float* gtab, const int64_t* step_dev, int gstride, int goff,
+                           int64_t n, void* stream);
 
 /* Westervelt stage helpers (cuda/demo_nonlinear_bowl.py:603-650):
  *   w = vn*vn                                                   (:603)
@@ -187,14 +198,15 @@ int fus_westervelt_mass_f64(const double* un, const double* vn, const double* c2
 int fus_westervelt_mass_f32(const float* un, const float* vn, const float* c2, const float* c5,
                             float* m, float* b, const float* detJ, const int32_t* dofmap,
                             int64_t ncells, int ncols, void* stream);
-/* kv = b / (m + m0); u += bdt*ku; v += bdt*kv; then as fus_rk_close (also zeroes m). */
+/* kv = b / (m + m0); u += bdt*ku; v += bdt*kv; m = 0; then as fus_rk_close. */
 int fus_rk_close_westervelt_f64(double* u, double* v, double* u0, double* v0, double* ku,
                                 double* kv, double* un, double* b, double* m, const double* m0,
                                 double bdt, double adt_next, int next_mode, int64_t n,
-                                void* stream);
+                                int64_t* step_dev, void* stream);
 int fus_rk_close_westervelt_f32(float* u, float* v, float* u0, float* v0, float* ku, float* kv,
                                 float* un, float* b, float* m, const float* m0, float bdt,
-                                float adt_next, int next_mode, int64_t n, void* stream);
+                                float adt_next, int next_mode, int64_t n, int64_t* step_dev,
+                                void* stream);
 
 /* --------------------------------------------------------------------- *
  * Geometry precompute on the device - cuda/precompute.py:17-163
