@@ -9,21 +9,30 @@
 //     y_j  = sum_d sum_q D[q, j_d] f_d[.. q ..]             (:171-187)
 //     y[dofmap] += y_j                                      (:190)
 //
-// Design (B200 first):
+// Design (B200 first).  ncu on the first version of this kernel showed the
+// L1/shared-memory data pipe (not HBM, not FP64) as the limiter, so the kernel
+// is organised to minimise shared-memory wavefronts per cell:
 //   * persistent CTAs, one batch of B cells per iteration, n^2 threads per
-//     cell: thread (j,k) owns the whole i-column of its cell in registers, so
-//     the x-direction contractions are pure register FMAs with the D entries
-//     as constant-bank operands; only the y/z directions read shared memory;
-//   * G (the dominant HBM stream, 6*n^3 values per cell) and the dofmap block
-//     of the NEXT batch are fetched by the TMA unit with 1-D bulk copies
-//     (cp.async.bulk + mbarrier complete_tx) into a 2-stage shared-memory
-//     ring while the current batch computes: the reference's AoS layout
-//     [cell][q][6] is accepted as is and read from shared memory with
-//     conflict-free 16-byte loads (lane stride 48 B in fp64, 24 B in fp32);
-//   * f1, f2 are written back IN PLACE into the thread's own (dead) G record,
-//     so the only extra tile is the n^3 gather/scatter tile;
-//   * gather and scatter are cooperative and index-contiguous (coalesced
-//     dofmap reads from smem, fire-and-forget RED atomics or plain RMW when
+//     cell.  Every 1-D contraction is done by the thread that owns the whole
+//     pencil along the contraction direction, in registers, with the entries
+//     of D as compile-time constant-bank operands: thread (j,k) owns x
+//     pencils, thread (i,k) owns y pencils, thread (i,j) owns z pencils.
+//     Moving between the three ownerships costs one write + one read of the
+//     tile (n values per thread) instead of n^2 operand loads per thread;
+//   * two shared-memory tiles per cell with different paddings, UY (plane
+//     stride = n mod M) and UZ (plane stride = 1 mod M, M = banks per
+//     wavefront), make ALL access patterns of the three ownerships
+//     bank-conflict free (tools/smem_layout_search.py);
+//   * G (the dominant HBM stream, 6*n^3 values per cell) of the NEXT batch is
+//     fetched by the TMA unit (cp.async.bulk + mbarrier complete_tx, one copy
+//     per cell into a slot padded so that 16-byte AoS record loads stay
+//     conflict free across cell boundaries) into a 2-stage ring while the
+//     current batch computes; the reference's AoS layout [cell][q][6] is
+//     accepted as is;
+//   * the dofmap entries and the gathered x values of the NEXT batch are
+//     prefetched into registers (each thread gathers and scatters exactly its
+//     own x pencil, coalesced over (j,k)), so no global-load latency is exposed
+//     inside a batch; scatter is fire-and-forget RED atomics (or plain RMW when
 //     the caller colours the cells).
 //
 // HBM-bound: algorithmic bytes per cell = Nd*4 (dofmap) + 6*Nd*s (G) + s
@@ -47,7 +56,7 @@ struct DTable<float, P> {
   static __device__ __forceinline__ float at(int i) { return c_D32[P - 2][i]; }
 };
 
-// cells per CTA batch / threads per CTA, per (n, sizeof T)
+// cells per CTA batch / threads per CTA / min CTAs per SM, per (n, sizeof T)
 template <typename T, int n>
 struct Cfg;
 #define FUS_CFG(TYPE, N, BCELLS, THREADS_, MINB_)       \
@@ -73,18 +82,30 @@ FUS_CFG(float, 8, 2, 128, 3)
 
 constexpr int kStages = 2;
 
+constexpr int ceil_cong(int lo, int r, int M) {  // smallest v >= lo with v = r (mod M)
+  return lo + (((r - lo) % M) + M) % M;
+}
+
 template <typename T, int n>
 struct Layout {
+  static constexpr int S = (int)sizeof(T);
   static constexpr int B = Cfg<T, n>::B;
+  static constexpr int N2 = n * n;
   static constexpr int Nd = n * n * n;
-  static constexpr int GBYTES = B * Nd * 6 * (int)sizeof(T);
-  static constexpr int GSLOT = ((GBYTES + 15) & ~15) + 16;
-  static constexpr int DBYTES = B * Nd * 4;
-  static constexpr int DSLOT = ((DBYTES + 15) & ~15) + 16;
-  static constexpr int STAGE = GSLOT + DSLOT;
-  static constexpr int TILE = ((B * Nd * (int)sizeof(T) + 15) & ~15);
-  static constexpr int BAR = 64;
-  static constexpr int SMEM = BAR + kStages * STAGE + TILE;
+  // tile strides in elements (see header comment); M lanes share a wavefront
+  static constexpr int M = S == 8 ? 16 : 32;
+  static constexpr int SPY = ceil_cong(N2, n % M, M);
+  static constexpr int SCY = n * SPY;
+  static constexpr int SPZ = ceil_cong(N2, 1, M);
+  static constexpr int SCZ = ceil_cong(n * SPZ, N2 % M, M);
+  // G staging: per-cell record block of CB bytes at stride GC bytes
+  static constexpr int CB = Nd * 6 * S;
+  static constexpr int GC = ceil_cong(CB + 16, (N2 * 6 * S) % 128, 128);
+  static constexpr int STAGE = ((B * GC + 32 + 127) / 128) * 128;
+  static constexpr int BAR = 128;
+  static constexpr int TILE_Y = ((B * SCY * S + 127) / 128) * 128;
+  static constexpr int TILE_Z = ((B * SCZ * S + 127) / 128) * 128;
+  static constexpr int SMEM = BAR + kStages * STAGE + TILE_Y + TILE_Z;
 };
 
 template <typename T>
@@ -97,7 +118,7 @@ struct StiffArgs {
   const T* G;
   const int32_t* dofmap;
   long long ncells;
-  int bulk_ok;  // G and dofmap base pointers are 16-byte aligned
+  int bulk_ok;  // G base aligned for the 2-element vector loads of the AoS records
 };
 
 template <typename T>
@@ -118,12 +139,6 @@ __device__ __forceinline__ G6<float> load_g6(const float* p) {
   const float2 c = *reinterpret_cast<const float2*>(p + 4);
   return {a.x, a.y, b.x, b.y, c.x, c.y};
 }
-__device__ __forceinline__ void store_f12(double* p, double f1, double f2) {
-  *reinterpret_cast<double2*>(p) = make_double2(f1, f2);
-}
-__device__ __forceinline__ void store_f12(float* p, float f1, float f2) {
-  *reinterpret_cast<float2*>(p) = make_float2(f1, f2);
-}
 
 template <typename T, int n, bool DUAL, bool ATOMIC>
 __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
@@ -132,30 +147,28 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
   using D = DTable<T, n - 1>;
   constexpr int B = L::B;
   constexpr int Nd = L::Nd;
-  constexpr int N2 = n * n;
+  constexpr int N2 = L::N2;
   constexpr int THREADS = Cfg<T, n>::THREADS;
-  constexpr int PER_THREAD = (B * Nd + THREADS - 1) / THREADS;
+  static_assert(B * N2 <= THREADS, "one thread per (cell, j, k)");
 
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   unsigned char* stages = smem + L::BAR;
-  T* tile = reinterpret_cast<T*>(smem + L::BAR + kStages * L::STAGE);
+  T* UY = reinterpret_cast<T*>(smem + L::BAR + kStages * L::STAGE);
+  T* UZ = reinterpret_cast<T*>(smem + L::BAR + kStages * L::STAGE + L::TILE_Y);
 
   const int tid = threadIdx.x;
   const int cs = tid / N2;  // cell slot within the batch
   const int t2 = tid - cs * N2;
-  const int j = t2 / n;
-  const int k = t2 - j * n;
+  const int ra = t2 / n;  // the two pencil coordinates this thread plays
+  const int rb = t2 - ra * n;
+  const bool lane_ok = cs < B;
 
-  // rows / columns of D this thread needs for the y- and z-direction sums
-  T Dj[n], Dk[n], DTj[n], DTk[n];
-#pragma unroll
-  for (int l = 0; l < n; ++l) {
-    Dj[l] = D::at(j * n + l);
-    Dk[l] = D::at(k * n + l);
-    DTj[l] = D::at(l * n + j);
-    DTk[l] = D::at(l * n + k);
-  }
+  // tile bases for the three ownerships
+  T* const uy1 = UY + cs * L::SCY + t2;                  // + i*SPY : (j,k) = (ra,rb)
+  T* const uz1 = UZ + cs * L::SCZ + t2;                  // + i*SPZ
+  T* const uy2 = UY + cs * L::SCY + ra * L::SPY + rb;    // + j*n   : (i,k) = (ra,rb)
+  T* const uz3 = UZ + cs * L::SCZ + rb * L::SPZ + ra * n;  // + k    : (i,j) = (rb,ra)
 
   const long long nb = (a.ncells + B - 1) / B;
   const long long stride = gridDim.x;
@@ -167,154 +180,222 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
   }
   __syncthreads();
 
-  // A batch goes through the TMA unit when it is full, is not the last one of
-  // the array (the 16-byte rounding may read a few bytes past its end) and the
-  // base pointers are aligned.
+  // A batch goes through the TMA unit unless it is the last one of the array
+  // (ragged, and the 16-byte rounding may read a few bytes past the end).
   auto bulk_eligible = [&](long long b) { return a.bulk_ok && b < nb - 1; };
+  auto batch_shift = [&](long long b) {
+    return (unsigned)((reinterpret_cast<unsigned long long>(a.G) + (unsigned long long)b * B * L::CB) & 15ull);
+  };
 
   auto issue = [&](long long b, int s) {
-    // generic-proxy writes to this stage (in-place f1/f2) happened before the
-    // preceding __syncthreads; order them before the async-proxy refill
-    fence_proxy_async_smem();
+    fence_proxy_async_smem();  // generic reads of this stage (previous use) before the refill
     const unsigned long long g0 =
-        reinterpret_cast<unsigned long long>(a.G) + (unsigned long long)b * L::GBYTES;
-    const unsigned long long d0 =
-        reinterpret_cast<unsigned long long>(a.dofmap) + (unsigned long long)b * L::DBYTES;
-    const unsigned long long ga = g0 & ~15ull, ge = (g0 + L::GBYTES + 15ull) & ~15ull;
-    const unsigned long long da = d0 & ~15ull, de = (d0 + L::DBYTES + 15ull) & ~15ull;
+        reinterpret_cast<unsigned long long>(a.G) + (unsigned long long)b * B * L::CB;
+    const unsigned shift = (unsigned)(g0 & 15ull);
     unsigned char* st = stages + s * L::STAGE;
-    mbar_arrive_expect_tx(&full[s], (uint32_t)((ge - ga) + (de - da)));
-    bulk_g2s_hint(st, reinterpret_cast<const void*>(ga), (uint32_t)(ge - ga), &full[s],
-                  l2_policy_evict_first());
-    bulk_g2s(st + L::GSLOT, reinterpret_cast<const void*>(da), (uint32_t)(de - da), &full[s]);
+    unsigned total = 0;
+#pragma unroll
+    for (int c = 0; c < B; ++c) {
+      const unsigned long long src = g0 + (unsigned long long)c * L::CB;
+      total += (unsigned)(((src + L::CB + 15ull) & ~15ull) - (src & ~15ull));
+    }
+    mbar_arrive_expect_tx(&full[s], total);
+    const uint64_t pol = l2_policy_evict_first();
+#pragma unroll
+    for (int c = 0; c < B; ++c) {
+      const unsigned long long src = g0 + (unsigned long long)c * L::CB;
+      const unsigned long long sa = src & ~15ull, se = (src + L::CB + 15ull) & ~15ull;
+      bulk_g2s_hint(st + shift + c * L::GC - (unsigned)(src & 15ull), reinterpret_cast<const void*>(sa),
+                    (uint32_t)(se - sa), &full[s], pol);
+    }
   };
+
+  // ---- register prefetch of the dofmap / x pencil of a batch ----------------
+  auto load_dofs = [&](long long b, int (&dof)[n]) {
+    const long long cell = b * B + cs;
+    if (lane_ok && b < nb && cell < a.ncells) {
+      const int32_t* dm = a.dofmap + cell * (long long)Nd + t2;
+#pragma unroll
+      for (int i = 0; i < n; ++i) dof[i] = __ldg(dm + i * N2);
+    } else {
+#pragma unroll
+      for (int i = 0; i < n; ++i) dof[i] = -1;
+    }
+  };
+  auto load_x = [&](const int (&dof)[n], T (&xa)[n], T (&xb)[n]) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      xa[i] = T(0);
+      if constexpr (DUAL) xb[i] = T(0);
+      if (dof[i] >= 0) {
+        xa[i] = __ldg(a.xa + dof[i]);
+        if constexpr (DUAL) xb[i] = __ldg(a.xb + dof[i]);
+      }
+    }
+  };
+
+  int dof[n], dofn[n];
+  T xv[n], xw[n], xvn[n], xwn[n];  // xw*: second vector in dual mode
+  (void)xw;
+  (void)xwn;
 
   // prologue: first batch of this CTA
   if (tid == 0 && (long long)blockIdx.x < nb && bulk_eligible(blockIdx.x)) issue(blockIdx.x, 0);
+  load_dofs(blockIdx.x, dof);
+  load_x(dof, xv, xw);
 
   int it = 0;
   for (long long b = blockIdx.x; b < nb; b += stride, ++it) {
     const int s = it & 1;
-    // prefetch the next batch into the other stage (consumed last iteration)
-    if (tid == 0) {
-      const long long bn = b + stride;
-      if (bn < nb && bulk_eligible(bn)) issue(bn, s ^ 1);
-    }
+    const long long bn = b + stride;
+    // TMA prefetch of the next batch into the other stage (consumed last iteration)
+    if (tid == 0 && bn < nb && bulk_eligible(bn)) issue(bn, s ^ 1);
 
     unsigned char* st = stages + s * L::STAGE;
     const long long cell0 = b * B;
     const int ncur = (int)((a.ncells - cell0) < (long long)B ? (a.ncells - cell0) : (long long)B);
-    T* Gs;
-    const int32_t* dm;
-    if (bulk_eligible(b)) {
-      const unsigned long long g0 =
-          reinterpret_cast<unsigned long long>(a.G) + (unsigned long long)b * L::GBYTES;
-      const unsigned long long d0 =
-          reinterpret_cast<unsigned long long>(a.dofmap) + (unsigned long long)b * L::DBYTES;
-      Gs = reinterpret_cast<T*>(st + (g0 & 15ull));
-      dm = reinterpret_cast<const int32_t*>(st + L::GSLOT + (d0 & 15ull));
-      mbar_wait(&full[s], (uint32_t)((it >> 1) & 1));
-    } else {
-      // tail / unaligned: cooperative loads through the generic proxy
-      Gs = reinterpret_cast<T*>(st);
-      int32_t* dmw = reinterpret_cast<int32_t*>(st + L::GSLOT);
+    const bool active = lane_ok && cs < ncur;
+    const bool bulk = bulk_eligible(b);
+    const T* Gs = reinterpret_cast<const T*>(st + (bulk ? batch_shift(b) : 0u));
+    if (!bulk) {
+      // tail batch / unaligned base: cooperative loads through the generic proxy
       const T* gsrc = a.G + cell0 * (long long)(Nd * 6);
-      const int32_t* dsrc = a.dofmap + cell0 * (long long)Nd;
-      for (int idx = tid; idx < ncur * Nd * 6; idx += THREADS) Gs[idx] = gsrc[idx];
-      for (int idx = tid; idx < ncur * Nd; idx += THREADS) dmw[idx] = dsrc[idx];
-      dm = dmw;
-      __syncthreads();
+      T* gdst = reinterpret_cast<T*>(st);
+      for (int idx = tid; idx < ncur * Nd * 6; idx += THREADS) {
+        const int c = idx / (Nd * 6);
+        gdst[c * (L::GC / L::S) + (idx - c * Nd * 6)] = gsrc[idx];
+      }
     }
 
-    // ---- gather x[dofmap] into the tile (index-contiguous) ----------------
-    {
-      T val[PER_THREAD];
+    // next batch's dofmap entries: in flight during this whole batch
+    load_dofs(bn, dofn);
+
+    // ---- x pencil (registers) -> tiles; x-direction gradient ----------------
+    T gx[n];
+    T cc = T(1);
+    if (active) {
+      if constexpr (DUAL) {
+        const T ca = a.ca[cell0 + cs], cb = a.cb[cell0 + cs];
 #pragma unroll
-      for (int r = 0; r < PER_THREAD; ++r) {
-        const int idx = tid + r * THREADS;
-        val[r] = T(0);
-        if (idx < ncur * Nd) {
-          const int dof = dm[idx];
-          if constexpr (DUAL) {
-            const long long c = cell0 + idx / Nd;
-            val[r] = a.ca[c] * a.xa[dof] + a.cb[c] * a.xb[dof];
-          } else {
-            val[r] = a.xa[dof];
-          }
-        }
+        for (int i = 0; i < n; ++i) xv[i] = ca * xv[i] + cb * xw[i];
+      } else {
+        cc = a.ca[cell0 + cs];
       }
 #pragma unroll
-      for (int r = 0; r < PER_THREAD; ++r) {
-        const int idx = tid + r * THREADS;
-        if (idx < B * Nd) tile[idx] = val[r];
+      for (int i = 0; i < n; ++i) {
+        uy1[i * L::SPY] = xv[i];
+        uz1[i * L::SPZ] = xv[i];
+      }
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        T acc = T(0);
+#pragma unroll
+        for (int l = 0; l < n; ++l) acc += D::at(i * n + l) * xv[l];
+        gx[i] = acc;
       }
     }
     __syncthreads();
 
-    const bool active = cs < ncur;
+    // ---- y pencils (i,k) = (ra,rb); z pencils (i,j) = (rb,ra) ---------------
+    T gy[n], gz[n];
+    if (active) {
+      T u[n];
+#pragma unroll
+      for (int l = 0; l < n; ++l) u[l] = uy2[l * n];
+#pragma unroll
+      for (int j = 0; j < n; ++j) {
+        T acc = T(0);
+#pragma unroll
+        for (int l = 0; l < n; ++l) acc += D::at(j * n + l) * u[l];
+        gy[j] = acc;
+      }
+#pragma unroll
+      for (int l = 0; l < n; ++l) u[l] = uz3[l];
+#pragma unroll
+      for (int k = 0; k < n; ++k) {
+        T acc = T(0);
+#pragma unroll
+        for (int l = 0; l < n; ++l) acc += D::at(k * n + l) * u[l];
+        gz[k] = acc;
+      }
+    }
+    __syncthreads();  // every pencil has been read: overwrite u with the gradients
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < n; ++j) uy2[j * n] = gy[j];
+#pragma unroll
+      for (int k = 0; k < n; ++k) uz3[k] = gz[k];
+    }
+    if (bulk) mbar_wait(&full[s], (uint32_t)((it >> 1) & 1));
+    __syncthreads();
+
+    // ---- geometric transform at (i, j, k), (j,k) = (ra,rb); x-direction D^T --
     T ry[n];
     if (active) {
-      const T* tl = tile + cs * Nd;
-      T* Gc = Gs + cs * (Nd * 6);
-      T cc = T(1);
-      if constexpr (!DUAL) cc = a.ca[cell0 + cs];
-      T ru[n];
+      const T* Gc = Gs + cs * (L::GC / L::S) + t2 * 6;
 #pragma unroll
-      for (int l = 0; l < n; ++l) {
-        ru[l] = tl[l * N2 + t2];
-        ry[l] = T(0);
-      }
+      for (int l = 0; l < n; ++l) ry[l] = T(0);
 #pragma unroll
       for (int i = 0; i < n; ++i) {
-        T gx = T(0), gy = T(0), gz = T(0);
-#pragma unroll
-        for (int l = 0; l < n; ++l) gx += D::at(i * n + l) * ru[l];
-#pragma unroll
-        for (int l = 0; l < n; ++l) gy += Dj[l] * tl[i * N2 + l * n + k];
-#pragma unroll
-        for (int l = 0; l < n; ++l) gz += Dk[l] * tl[i * N2 + j * n + l];
-        T* gq = Gc + (i * N2 + t2) * 6;
-        const G6<T> g = load_g6(gq);
-        const T f0 = cc * (g.g0 * gx + g.g1 * gy + g.g2 * gz);
-        const T f1 = cc * (g.g1 * gx + g.g3 * gy + g.g4 * gz);
-        const T f2 = cc * (g.g2 * gx + g.g4 * gy + g.g5 * gz);
+        const T wy = uy1[i * L::SPY];
+        const T wz = uz1[i * L::SPZ];
+        const G6<T> g = load_g6(Gc + i * (N2 * 6));
+        const T f0 = cc * (g.g0 * gx[i] + g.g1 * wy + g.g2 * wz);
+        const T f1 = cc * (g.g1 * gx[i] + g.g3 * wy + g.g4 * wz);
+        const T f2 = cc * (g.g2 * gx[i] + g.g4 * wy + g.g5 * wz);
 #pragma unroll
         for (int l = 0; l < n; ++l) ry[l] += D::at(i * n + l) * f0;
-        store_f12(gq, f1, f2);  // in place: this record is dead now
+        uy1[i * L::SPY] = f1;
+        uz1[i * L::SPZ] = f2;
+      }
+    }
+    // next batch's x pencil: its dofmap entries have landed by now
+    load_x(dofn, xvn, xwn);
+    __syncthreads();
+
+    // ---- D^T along y and z, in place (each thread rewrites its own pencil) --
+    if (active) {
+      T f[n];
+#pragma unroll
+      for (int l = 0; l < n; ++l) f[l] = uy2[l * n];
+#pragma unroll
+      for (int j = 0; j < n; ++j) {
+        T acc = T(0);
+#pragma unroll
+        for (int l = 0; l < n; ++l) acc += D::at(l * n + j) * f[l];
+        uy2[j * n] = acc;
+      }
+#pragma unroll
+      for (int l = 0; l < n; ++l) f[l] = uz3[l];
+#pragma unroll
+      for (int k = 0; k < n; ++k) {
+        T acc = T(0);
+#pragma unroll
+        for (int l = 0; l < n; ++l) acc += D::at(l * n + k) * f[l];
+        uz3[k] = acc;
       }
     }
     __syncthreads();
 
+    // ---- sum the three directions and scatter-add the x pencil --------------
     if (active) {
-      const T* Gc = Gs + cs * (Nd * 6);
-      T* tl = tile + cs * Nd;
 #pragma unroll
       for (int i = 0; i < n; ++i) {
-        T acc = ry[i];
-#pragma unroll
-        for (int l = 0; l < n; ++l) acc += DTj[l] * Gc[(i * N2 + l * n + k) * 6];
-#pragma unroll
-        for (int l = 0; l < n; ++l) acc += DTk[l] * Gc[(i * N2 + j * n + l) * 6 + 1];
-        tl[i * N2 + t2] = acc;
-      }
-    }
-    __syncthreads();
-
-    // ---- scatter-add the tile into y ---------------------------------------
-#pragma unroll
-    for (int r = 0; r < PER_THREAD; ++r) {
-      const int idx = tid + r * THREADS;
-      if (idx < ncur * Nd) {
-        const int dof = dm[idx];
+        const T val = ry[i] + uy1[i * L::SPY] + uz1[i * L::SPZ];
         if constexpr (ATOMIC) {
-          atomicAdd(a.y + dof, tile[idx]);
+          atomicAdd(a.y + dof[i], val);
         } else {
-          a.y[dof] += tile[idx];
+          a.y[dof[i]] += val;
         }
       }
     }
-    fence_proxy_async_smem();  // generic accesses to stage s before its TMA refill
-    __syncthreads();           // tile and stage s are free again
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      dof[i] = dofn[i];
+      xv[i] = xvn[i];
+      if constexpr (DUAL) xw[i] = xwn[i];
+    }
+    __syncthreads();  // tiles and stage s are free again
   }
 }
 
@@ -391,7 +472,7 @@ int stiffness_entry(const T* xa, const T* ca, const T* xb, const T* cb, T* y, co
   a.G = G;
   a.dofmap = dofmap;
   a.ncells = ncells;
-  a.bulk_ok = ((reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(dofmap)) & 15u) == 0;
+  a.bulk_ok = (reinterpret_cast<uintptr_t>(G) & (2 * sizeof(T) - 1)) == 0;  // 16-byte record loads
   return dual ? launch<T, true>(a, P, flags, st) : launch<T, false>(a, P, flags, st);
 }
 

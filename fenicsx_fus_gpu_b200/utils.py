@@ -1,0 +1,163 @@
+"""
+Utils - index maps for the halo exchange and facet integration domains
+======================================================================
+
+Drop-in for the hot-path half of ``/root/reference/cuda/utils.py``:
+
+* ``compute_scatterer_data(index_map)`` (:8-78) - same return value, bit for
+  bit, but vectorised: the reference's O(ranks * size_local) Python loop over
+  ``shared_dofs.links(dof)`` (:43-47) is one ``np.unique(..., return_counts)``,
+  and the ghost-index exchange runs over ``torch.distributed`` (one process
+  per GPU) instead of mpi4py.
+* ``facet_integration_domain(facets, mesh)`` (:81-114) - vectorised over the
+  facets, same ``(cell, local facet)`` rows.
+* ``compute_diffusivity_of_sound`` (:157-162).
+
+Pure host integer work; nothing here touches the GPU.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+
+def _owner_lists(index_map):
+    """Ghost positions grouped by owner (cuda/utils.py:23-37).  ``np.argsort``
+    with the default (unstable) kind on the same input, as the reference does,
+    so the order inside a group is reproduced exactly."""
+    owners = np.asarray(index_map.owners)
+    unique_owners, owners_size = np.unique(owners, return_counts=True)
+    owners_argsorted = np.argsort(owners)
+    owners_offsets = np.insert(np.cumsum(owners_size), 0, 0)
+    owners_idx = [owners_argsorted[owners_offsets[i]:owners_offsets[i + 1]]
+                  for i in range(unique_owners.size)]
+    return owners_idx, owners_size, unique_owners
+
+
+def _ghost_ranks(index_map):
+    """Ranks that ghost my owned dofs and how many each (cuda/utils.py:39-52).
+
+    The reference appends ``shared_rank`` once per owned dof whose destination
+    list contains it, then takes ``np.unique(..., return_counts=True)``: that is
+    the histogram of ``index_to_dest_ranks().array``.
+    """
+    shared = index_map.index_to_dest_ranks()
+    arr = np.asarray(shared.array)
+    if arr.size == 0:
+        # np.unique(np.array([])) in the reference: float64 empties
+        return np.unique(np.array([]), return_counts=True)
+    return np.unique(arr, return_counts=True)
+
+
+def compute_scatterer_data(index_map, comm=None):
+    """Extract scatterer data - cuda/utils.py:8-78.
+
+    ``comm`` is a ``torch.distributed`` process group (default: the world
+    group).  With a single process (or no initialised process group) there are
+    no neighbours and both lists are empty.
+
+    Returns ``owners_data = [owners_idx, owners_size, unique_owners]`` and
+    ``ghosts_data = [ghosts_idx, ghosts_size, unique_ghosts]``.
+    """
+    owners_idx, owners_size, unique_owners = _owner_lists(index_map)
+    unique_ghosts, ghosts_size = _ghost_ranks(index_map)
+    ghosts_np = np.asarray(index_map.ghosts)
+
+    send = [np.ascontiguousarray(ghosts_np[idx], dtype=np.int64) for idx in owners_idx]
+    recv = exchange_index_lists(send, unique_owners, ghosts_size, unique_ghosts, comm)
+    ghosts_idx = [r - index_map.local_range[0] for r in recv]
+
+    owners_data = [owners_idx, owners_size, unique_owners]
+    ghosts_data = [ghosts_idx, ghosts_size, unique_ghosts]
+    return owners_data, ghosts_data
+
+
+def exchange_index_lists(send, dests, recv_sizes, sources, comm=None):
+    """The ``Isend/Irecv/Waitall`` round of cuda/utils.py:57-71 over
+    ``torch.distributed`` point-to-point ops (gloo on CPU tensors; for NCCL
+    the int64 lists are staged through the device)."""
+    if len(send) == 0 and len(sources) == 0:
+        return []
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        raise RuntimeError("index map has neighbours but torch.distributed is not initialised")
+    backend = dist.get_backend(comm)
+    device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    sbuf = [torch.from_numpy(s).to(device) for s in send]
+    rbuf = [torch.empty(int(n), dtype=torch.int64, device=device) for n in recv_sizes]
+    ops = []
+    for t, dst in zip(sbuf, dests):
+        ops.append(dist.P2POp(dist.isend, t, _global_rank(int(dst), comm), group=comm))
+    for t, src in zip(rbuf, sources):
+        ops.append(dist.P2POp(dist.irecv, t, _global_rank(int(src), comm), group=comm))
+    for r in dist.batch_isend_irecv(ops):
+        r.wait()
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+    return [t.cpu().numpy() for t in rbuf]
+
+
+def _global_rank(group_rank: int, comm):
+    import torch.distributed as dist
+
+    if comm is None or comm is dist.group.WORLD:
+        return group_rank
+    return dist.get_global_rank(comm, group_rank)
+
+
+def compute_scatterer_data_all(index_maps):
+    """All ranks at once in one process (used where ranks are emulated on one
+    host: fixtures, single-process multi-partition tests)."""
+    pre = []
+    sent = {}
+    for rank, im in enumerate(index_maps):
+        owners_idx, owners_size, unique_owners = _owner_lists(im)
+        unique_ghosts, ghosts_size = _ghost_ranks(im)
+        ghosts_np = np.asarray(im.ghosts)
+        for idx, owner in zip(owners_idx, unique_owners):
+            sent[(rank, int(owner))] = np.ascontiguousarray(ghosts_np[idx], dtype=np.int64)
+        pre.append((owners_idx, owners_size, unique_owners, ghosts_size, unique_ghosts))
+    out = []
+    for rank, im in enumerate(index_maps):
+        owners_idx, owners_size, unique_owners, ghosts_size, unique_ghosts = pre[rank]
+        ghosts_idx = [sent[(int(g), rank)] - im.local_range[0] for g in unique_ghosts]
+        out.append(([owners_idx, owners_size, unique_owners], [ghosts_idx, ghosts_size, unique_ghosts]))
+    return out
+
+
+def facet_integration_domain(facets, mesh):
+    """``boundary_data[i] = (cell, local facet)`` - cuda/utils.py:81-114.
+
+    ``mesh`` is a DOLFINx mesh (``mesh.topology.connectivity``) - the same
+    look-ups as the reference, vectorised over the facets through the
+    adjacency arrays instead of per-facet ``links`` calls.  (Box meshes of the
+    synthetic substrate use ``substrate.boundary_facets`` which yields the
+    same rows directly.)
+    """
+    facets = np.asarray(facets, dtype=np.int32)
+    tdim = mesh.topology.dim
+    c2f = mesh.topology.connectivity(tdim, tdim - 1)
+    f2c = mesh.topology.connectivity(tdim - 1, tdim)
+    f2c_off = np.asarray(f2c.offsets)
+    f2c_arr = np.asarray(f2c.array)
+    cells = f2c_arr[f2c_off[facets]].astype(np.int32)  # links(facet)[0]
+    c2f_off = np.asarray(c2f.offsets)
+    c2f_arr = np.asarray(c2f.array)
+    nfc = int(c2f_off[1] - c2f_off[0]) if c2f_off.size > 1 else 0
+    boundary_data = np.zeros((facets.size, 2), dtype=np.int32)
+    if facets.size == 0:
+        return boundary_data
+    # cells of one type have the same number of facets: rows of the cell->facet table
+    rows = c2f_arr[c2f_off[cells][:, None] + np.arange(nfc)[None, :]]
+    local = np.argmax(rows == facets[:, None], axis=1)  # first match, as np.where(...)[0][0]
+    boundary_data[:, 0] = cells
+    boundary_data[:, 1] = local
+    return boundary_data
+
+
+def compute_diffusivity_of_sound(w0: float, c0: float, alpha: float) -> float:
+    """``delta = 2 alpha c0^3 / w0^2`` with alpha in dB/m converted to Np/m -
+    cuda/utils.py:157-162."""
+    return 2.0 * (alpha / 20.0 * np.log(10.0)) * c0**3 / w0**2
