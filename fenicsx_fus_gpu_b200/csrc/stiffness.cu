@@ -234,7 +234,13 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
     }
   };
 
-  int dof[n], dofn[n];
+  // Register pipeline, two batches deep so that no load depends on another load
+  // issued in the same batch (the compiler is free to hoist these read-only
+  // loads to the top of the loop body):
+  //   dof  : this batch (scatter)          xv : this batch's x pencil
+  //   dofn : next batch (x gather below)   xvn: next batch's x pencil (in flight)
+  //   dofm : the batch after (in flight)
+  int dof[n], dofn[n], dofm[n];
   T xv[n], xw[n], xvn[n], xwn[n];  // xw*: second vector in dual mode
   (void)xw;
   (void)xwn;
@@ -242,6 +248,7 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
   // prologue: first batch of this CTA
   if (tid == 0 && (long long)blockIdx.x < nb && bulk_eligible(blockIdx.x)) issue(blockIdx.x, 0);
   load_dofs(blockIdx.x, dof);
+  load_dofs(blockIdx.x + stride, dofn);
   load_x(dof, xv, xw);
 
   int it = 0;
@@ -267,8 +274,10 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
       }
     }
 
-    // next batch's dofmap entries: in flight during this whole batch
-    load_dofs(bn, dofn);
+    // in flight during this whole batch: the dofmap entries of the batch after
+    // next and the x pencil of the next batch (its entries arrived a batch ago)
+    load_dofs(bn + stride, dofm);
+    load_x(dofn, xvn, xwn);
 
     // ---- x pencil (registers) -> tiles; x-direction gradient ----------------
     T gx[n];
@@ -349,8 +358,6 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
         uz1[i * L::SPZ] = f2;
       }
     }
-    // next batch's x pencil: its dofmap entries have landed by now
-    load_x(dofn, xvn, xwn);
     __syncthreads();
 
     // ---- D^T along y and z, in place (each thread rewrites its own pencil) --
@@ -392,6 +399,7 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
 #pragma unroll
     for (int i = 0; i < n; ++i) {
       dof[i] = dofn[i];
+      dofn[i] = dofm[i];
       xv[i] = xvn[i];
       if constexpr (DUAL) xw[i] = xwn[i];
     }

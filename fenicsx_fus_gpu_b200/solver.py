@@ -1,0 +1,428 @@
+"""
+Solver - the explicit RK4 hot loops, fused
+==========================================
+
+``LinearSpectral3D`` replaces the time loop of
+``/root/reference/cuda/demo_linear_box.py:487-567`` (and ``demo_linear_piston.py``;
+CPU twin ``numba-cpu/demo_linear_box.py:389-459``; C++ ``LinearSpectral3D`` in
+``cpp/common/Linear.hpp:43-344`` whose name and ``init`` / ``rk4`` methods it keeps).
+``WesterveltSpectral3D`` replaces ``cuda/demo_nonlinear_bowl.py:529-657`` (and
+``demo_nonlinear_box.py``).
+
+What the reference does per RK stage with ~17 kernel launches, >= 8 device
+synchronisations and 3-5 host-staged MPI rounds becomes
+
+    [halo forward (un, vn) - one grouped NCCL round]
+    stiffness (scatter fused)  + boundary-facet diagonals (+ Westervelt cell mass pair)
+    [halo reverse (b[, m])]
+    close  (b/m, u,v updates, next stage's un/vn, b = 0  - ONE pass over the vectors)
+
+i.e. 3 launches per stage on one GPU, no host synchronisation, and a whole
+time step (4 stages) is captured once as a CUDA graph and replayed.  Source
+amplitudes come from a device table indexed by a device step counter, so a
+replay needs no host work at all.
+
+Reference quirks: the source is evaluated at the stage
+time ``tn`` as the numba-cpu / C++ paths do (Q1; ``source_at_stage_time=False``
+gives the CUDA demos' behaviour); the solution is ``u`` (Q2); vector kernels
+run over owned + ghost entries and ghost ``m`` keeps its partial sums (Q3).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, current_stream, fn
+
+A_RUNGE = (0.0, 0.5, 0.5, 1.0)
+B_RUNGE = (1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0)
+C_RUNGE = (0.0, 0.5, 0.5, 1.0)
+
+FUS_TABLES_RESIDENT = 1
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _tdt(dtype):
+    torch = _torch()
+    return {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32}[np.dtype(dtype)]
+
+
+def _dev(a, dtype=None):
+    """Device tensor of ``a`` (numpy is uploaded, device tensors pass through)."""
+    torch = _torch()
+    if isinstance(a, torch.Tensor):
+        t = a if a.is_cuda else a.cuda()
+    elif isinstance(a, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    else:
+        t = torch.as_tensor(a, device="cuda")
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def linear_source(t, f0, p0, c0, alpha=4.0):
+    """``g(t)`` of cuda/demo_linear_box.py:511-530 (numba-cpu :341-358)."""
+    T = 1.0 / f0
+    window = 0.5 * (1.0 - np.cos(f0 * np.pi * t / alpha)) if t < T * alpha else 1.0
+    return window * p0 * 2.0 * np.pi * f0 / c0 * np.cos(2.0 * np.pi * f0 * t), 0.0
+
+
+def westervelt_source(t, f0, p0, c0, alpha=4.0):
+    """``g(t), dg/dt`` of cuda/demo_nonlinear_bowl.py:556-594."""
+    T = 1.0 / f0
+    w0 = 2.0 * np.pi * f0
+    if t < T * alpha:
+        window = 0.5 * (1.0 - np.cos(f0 * np.pi * t / alpha))
+        dwindow = 0.5 * np.pi * f0 / alpha * np.sin(f0 * np.pi * t / alpha)
+    else:
+        window, dwindow = 1.0, 0.0
+    g = window * 2.0 * p0 * w0 / c0 * np.cos(w0 * t)
+    dg = dwindow * 2.0 * p0 * w0 / c0 * np.cos(w0 * t) - window * 2.0 * p0 * w0**2 / c0 * np.sin(w0 * t)
+    return g, dg
+
+
+class _RK4:
+    """State vectors, boundary diagonals, graph capture and the step loop shared
+    by the linear and Westervelt solvers."""
+
+    westervelt = False
+
+    def __init__(self, P, float_type, ndofs, dofmap, G, dphi_1D, halo=None, source=None,
+                 source_at_stage_time=True, use_graph=True):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.FusError("no CUDA device: this package has no CPU path")
+        self.P = int(P)
+        self.n = self.P + 1
+        self.dtype = np.dtype(float_type)
+        self.T = _tdt(self.dtype)
+        self.ndofs = int(ndofs)
+        self.dofmap = _dev(dofmap, torch.int32)
+        self.ncells = int(self.dofmap.shape[0])
+        self.G = _dev(G, self.T)
+        self.halo = halo
+        self.source = source
+        self.source_at_stage_time = bool(source_at_stage_time)
+        self.use_graph = bool(use_graph)
+        self._dphi_host = np.ascontiguousarray(
+            dphi_1D.cpu().numpy() if isinstance(dphi_1D, torch.Tensor) else dphi_1D, dtype=self.dtype)
+        z = lambda: torch.zeros(self.ndofs, dtype=self.T, device="cuda")  # noqa: E731
+        # the reference's 14 vectors (cuda/demo_linear_box.py:380-385, 464-471)
+        # shrink to 9: u v u0 v0 ku kv un b m  (vn lives in ku; g, u_n, v_n fused away)
+        self.u, self.v, self.u0, self.v0 = z(), z(), z(), z()
+        self.ku, self.kv, self.un, self.b = z(), z(), z(), z()
+        self.m = z()
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device="cuda")
+        self.gtab = None
+        self.t = 0.0
+        self.nstep = 0
+        self._graph = None
+        self._graph_dt = None
+        self._opened = False
+        self._bdofs = None
+        self._src = self._src2 = self._absb = None
+
+    # ---- set-up helpers ------------------------------------------------------
+    def _set_tables(self):
+        check(fn("fus_set_dphi", self.dtype)(self.P, self._dphi_host.ctypes.data, current_stream()),
+              "fus_set_dphi")
+
+    def _mass(self, x, coeff, y, detJ, dofmap):
+        if dofmap.shape[0]:
+            check(fn("fus_mass", self.dtype)(x.data_ptr(), coeff.data_ptr(), y.data_ptr(), detJ.data_ptr(),
+                                             dofmap.data_ptr(), dofmap.shape[0], dofmap.shape[1],
+                                             current_stream()), "fus_mass")
+
+    def _boundary_setup(self, terms):
+        """``terms``: list of (slot, bfacet_dofmap, detJ_f, facet_coeff) with slot in
+        {"src", "src2", "absb"}.  Builds the compact unique-dof list and the
+        diagonals = the facet mass operator applied to ones (cuda/demo_linear_box.py:546-551)."""
+        torch = _torch()
+        ones = torch.ones(self.ndofs, dtype=self.T, device="cuda")
+        dofs = [t[1].reshape(-1) for t in terms if t[1].shape[0]]
+        if not dofs:
+            self._bdofs = torch.zeros(0, dtype=torch.int32, device="cuda")
+            return
+        self._bdofs = torch.unique(torch.cat(dofs)).to(torch.int32).contiguous()
+        idx = self._bdofs.to(torch.int64)
+        for slot, bdm, dJ, coeff in terms:
+            if not bdm.shape[0]:
+                continue
+            tmp = torch.zeros(self.ndofs, dtype=self.T, device="cuda")
+            self._mass(ones, coeff, tmp, dJ, bdm)
+            setattr(self, "_" + slot, tmp[idx].contiguous())
+
+    # ---- stage pieces --------------------------------------------------------
+    def _ptr(self, t):
+        return None if t is None else t.data_ptr()
+
+    def _boundary(self, stage, g, dg, use_table):
+        nb = int(self._bdofs.numel())
+        if not nb:
+            return
+        check(fn("fus_boundary_terms", self.dtype)(
+            self.b.data_ptr(), self.ku.data_ptr(), self._bdofs.data_ptr(), self._ptr(self._src),
+            self._ptr(self._src2), self._ptr(self._absb), float(g), float(dg),
+            self.gtab.data_ptr() if use_table else None,
+            self.step_dev.data_ptr() if use_table else None, 8, 2 * stage, nb, current_stream()),
+            "fus_boundary_terms")
+
+    def _open_first(self):
+        """u0 = u, v0 = v, un = u0, vn(=ku) = v0, b = 0  (cuda/demo_linear_box.py:491-508 at a_0 = 0)."""
+        self.ku.zero_()
+        self.kv.zero_()
+        check(fn("fus_rk_open", self.dtype)(
+            self.u.data_ptr(), self.v.data_ptr(), self.u0.data_ptr(), self.v0.data_ptr(),
+            self.ku.data_ptr(), self.kv.data_ptr(), self.un.data_ptr(), self.b.data_ptr(), 0.0, 1,
+            self.ndofs, current_stream()), "fus_rk_open")
+        self._opened = True
+
+    def _assemble(self, stage, g, dg, use_table):  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def _close(self, stage, dt, count_step):  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def _halo_forward(self):
+        if self.halo is not None:
+            self.halo.forward(self.un, self.ku)
+
+    def _halo_reverse(self):
+        if self.halo is not None:
+            if self.westervelt:
+                self.halo.reverse(self.b, self.m)
+            else:
+                self.halo.reverse(self.b)
+
+    def _enqueue_step(self, dt, t, use_table):
+        for i in range(4):
+            g = dg = 0.0
+            if not use_table and self.source is not None:
+                g, dg = self.source(t + C_RUNGE[i] * dt if self.source_at_stage_time else t)
+            self._halo_forward()
+            self._assemble(i, g, dg, use_table)
+            self._halo_reverse()
+            self._close(i, dt, use_table)
+
+    # ---- public --------------------------------------------------------------
+    def init(self):
+        """Zero initial state (cpp/common/Linear.hpp:146-154)."""
+        for t in (self.u, self.v, self.u0, self.v0, self.ku, self.kv, self.un, self.b):
+            t.zero_()
+        self.t = 0.0
+        self.nstep = 0
+        self._opened = False
+
+    def source_table(self, t0, dt, nsteps):
+        """(nsteps, 8) table of (g, dg) per stage, times accumulated as the
+        reference does (``t += dt``)."""
+        tab = np.zeros((max(nsteps, 1), 8), dtype=self.dtype)
+        t = t0
+        for k in range(nsteps):
+            for i in range(4):
+                if self.source is not None:
+                    tab[k, 2 * i], tab[k, 2 * i + 1] = self.source(
+                        t + C_RUNGE[i] * dt if self.source_at_stage_time else t)
+            t += dt
+        return tab
+
+    def rk4(self, t0, dt, nsteps):
+        """``nsteps`` RK4 steps of size ``dt`` from ``t0``; returns the final time.
+        The device is NOT synchronised on return (stream ordered)."""
+        torch = _torch()
+        self._set_tables()
+        self.t = float(t0)
+        if not self._opened:
+            self._open_first()
+        if nsteps <= 0:
+            return self.t
+        self.gtab = _dev(self.source_table(self.t, dt, nsteps), self.T)
+        self.step_dev.zero_()
+        if self.use_graph:
+            if self._graph is None or self._graph_dt != dt or self._graph_tab != self.gtab.data_ptr():
+                self._capture(dt)
+            for _ in range(nsteps):
+                self._graph.replay()
+        else:
+            for k in range(nsteps):
+                self._enqueue_step(dt, 0.0, True)
+        for _ in range(nsteps):
+            self.t += dt
+        self.nstep += nsteps
+        return self.t
+
+    def step_eager(self, dt):
+        """One step with host-evaluated source scalars (no table, no graph)."""
+        self._set_tables()
+        if not self._opened:
+            self._open_first()
+        self._enqueue_step(dt, self.t, False)
+        self.t += dt
+        self.nstep += 1
+        return self.t
+
+    def _capture(self, dt):
+        torch = _torch()
+        # warm up outside capture (lazy NCCL communicators, module loading)
+        saved = [t.clone() for t in self._state()]
+        step0 = self.step_dev.clone()
+        self._enqueue_step(dt, 0.0, True)
+        torch.cuda.synchronize()
+        for t, s in zip(self._state(), saved):
+            t.copy_(s)
+        self.step_dev.copy_(step0)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._enqueue_step(dt, 0.0, True)
+        self._graph, self._graph_dt, self._graph_tab = g, dt, self.gtab.data_ptr()
+        # capture does not execute: state is still the saved one
+
+    def _state(self):
+        return [self.u, self.v, self.u0, self.v0, self.ku, self.kv, self.un, self.b, self.m]
+
+    # algorithmic HBM bytes of one RK stage
+    def stage_bytes(self):
+        s = self.dtype.itemsize
+        Nd = self.n**3
+        stiff = self.ncells * (Nd * 4 + 6 * Nd * s + s) + 2 * s * self.ndofs
+        return stiff + 14 * s * self.ndofs
+
+
+class LinearSpectral3D(_RK4):
+    """Linear second-order wave equation, explicit RK4, lumped mass
+    (cpp/common/Linear.hpp:43-344; cuda/demo_linear_box.py).
+
+    ``cell_coeff1 = 1/(rho c^2)`` (mass), ``cell_coeff2 = -1/rho`` (stiffness),
+    source facets ``(bfacet_dofmap1, detJ_f1, facet_coeff1 = 1/rho)``, absorbing
+    facets ``(bfacet_dofmap2, detJ_f2, facet_coeff2 = -1/(rho c))`` - the arrays of
+    cuda/demo_linear_box.py:336-345, on the device or as numpy.
+    """
+
+    def __init__(self, P, float_type, ndofs, dofmap, G, detJ, dphi_1D, cell_coeff1, cell_coeff2,
+                 bfacet_dofmap1=None, detJ_f1=None, facet_coeff1=None, bfacet_dofmap2=None,
+                 detJ_f2=None, facet_coeff2=None, halo=None, source=None,
+                 source_at_stage_time=True, use_graph=True):
+        super().__init__(P, float_type, ndofs, dofmap, G, dphi_1D, halo, source,
+                         source_at_stage_time, use_graph)
+        torch = _torch()
+        self.cell_coeff2 = _dev(cell_coeff2, self.T)
+        c1 = _dev(cell_coeff1, self.T)
+        dJ = _dev(detJ, self.T)
+        # lumped mass: fill(1) -> mass -> scatter_rev  (cuda/demo_linear_box.py:421-428)
+        ones = torch.ones(self.ndofs, dtype=self.T, device="cuda")
+        self._mass(ones, c1, self.m, dJ, self.dofmap)
+        if self.halo is not None:
+            self.halo.reverse(self.m)
+        terms = []
+        e = lambda w: torch.zeros((0, self.n**2), dtype=w, device="cuda")  # noqa: E731
+        bd1 = _dev(bfacet_dofmap1, torch.int32) if bfacet_dofmap1 is not None else e(torch.int32)
+        bd2 = _dev(bfacet_dofmap2, torch.int32) if bfacet_dofmap2 is not None else e(torch.int32)
+        if bd1.shape[0]:
+            terms.append(("src", bd1, _dev(detJ_f1, self.T), _dev(facet_coeff1, self.T)))
+        if bd2.shape[0]:
+            terms.append(("absb", bd2, _dev(detJ_f2, self.T), _dev(facet_coeff2, self.T)))
+        self._boundary_setup(terms)
+
+    def _assemble(self, stage, g, dg, use_table):
+        # b += K(-1/rho; un)                                  (cuda/demo_linear_box.py:543-545)
+        check(fn("fus_stiffness", self.dtype)(
+            self.un.data_ptr(), self.cell_coeff2.data_ptr(), self.b.data_ptr(), self.G.data_ptr(),
+            self.dofmap.data_ptr(), None, self.ncells, self.P, FUS_TABLES_RESIDENT, current_stream()),
+            "fus_stiffness")
+        # b += g * src + vn * absb                            (:546-551)
+        self._boundary(stage, g, dg, use_table)
+
+    def _close(self, stage, dt, count_step):
+        last = stage == 3
+        check(fn("fus_rk_close", self.dtype)(
+            self.u.data_ptr(), self.v.data_ptr(), self.u0.data_ptr(), self.v0.data_ptr(),
+            self.ku.data_ptr(), None, self.un.data_ptr(), self.b.data_ptr(), self.m.data_ptr(),
+            B_RUNGE[stage] * dt, 0.0 if last else A_RUNGE[stage + 1] * dt, 2 if last else 1,
+            self.ndofs, self.step_dev.data_ptr() if count_step else None, current_stream()),
+            "fus_rk_close")
+
+
+class WesterveltSpectral3D(_RK4):
+    """Westervelt equation (nonlinear, diffusive), explicit RK4 with a
+    state-dependent lumped mass - cuda/demo_nonlinear_bowl.py:358-374, 459-469,
+    529-657.
+
+    Cell coefficients ``c1 = 1/(rho c^2)``, ``c2 = -2 beta/(rho^2 c^4)``,
+    ``c3 = -1/rho``, ``c4 = -delta/(rho c^2)``, ``c5 = 2 beta/(rho^2 c^4)``; source
+    facets with ``facet_coeff1_1 = 1/rho`` (g) and ``facet_coeff2_1 = delta/(rho c^2)``
+    (dg/dt); absorbing facets with ``facet_coeff1_2 = delta/(rho c^3)`` (into m0)
+    and ``facet_coeff2_2 = -1/(rho c)``.
+    """
+
+    westervelt = True
+
+    def __init__(self, P, float_type, ndofs, dofmap, G, detJ, dphi_1D, cell_coeff1, cell_coeff2,
+                 cell_coeff3, cell_coeff4, cell_coeff5, bfacet_dofmap1=None, detJ_f1=None,
+                 facet_coeff1_1=None, facet_coeff2_1=None, bfacet_dofmap2=None, detJ_f2=None,
+                 facet_coeff1_2=None, facet_coeff2_2=None, halo=None, source=None,
+                 source_at_stage_time=True, use_graph=True):
+        super().__init__(P, float_type, ndofs, dofmap, G, dphi_1D, halo, source,
+                         source_at_stage_time, use_graph)
+        torch = _torch()
+        self.detJ = _dev(detJ, self.T)
+        self.c2, self.c3 = _dev(cell_coeff2, self.T), _dev(cell_coeff3, self.T)
+        self.c4, self.c5 = _dev(cell_coeff4, self.T), _dev(cell_coeff5, self.T)
+        c1 = _dev(cell_coeff1, self.T)
+        e = lambda w: torch.zeros((0, self.n**2), dtype=w, device="cuda")  # noqa: E731
+        bd1 = _dev(bfacet_dofmap1, torch.int32) if bfacet_dofmap1 is not None else e(torch.int32)
+        bd2 = _dev(bfacet_dofmap2, torch.int32) if bfacet_dofmap2 is not None else e(torch.int32)
+        # steady LHS m0 (cuda/demo_nonlinear_bowl.py:459-469)
+        ones = torch.ones(self.ndofs, dtype=self.T, device="cuda")
+        self.m0 = torch.zeros(self.ndofs, dtype=self.T, device="cuda")
+        self._mass(ones, c1, self.m0, self.detJ, self.dofmap)
+        if bd2.shape[0]:
+            self._mass(ones, _dev(facet_coeff1_2, self.T), self.m0, _dev(detJ_f2, self.T), bd2)
+        if self.halo is not None:
+            self.halo.reverse(self.m0)
+        terms = []
+        if bd1.shape[0]:
+            dJ1 = _dev(detJ_f1, self.T)
+            terms.append(("src", bd1, dJ1, _dev(facet_coeff1_1, self.T)))
+            terms.append(("src2", bd1, dJ1, _dev(facet_coeff2_1, self.T)))
+        if bd2.shape[0]:
+            terms.append(("absb", bd2, _dev(detJ_f2, self.T), _dev(facet_coeff2_2, self.T)))
+        self._boundary_setup(terms)
+        self.m.zero_()  # state-dependent part, accumulated per stage, zeroed by the close kernel
+
+    def _state(self):
+        return super()._state() + [self.m0]
+
+    def _assemble(self, stage, g, dg, use_table):
+        # m += M(c2; un)   and   b += M(c5; vn^2)   sharing detJ / dofmap   (:609-612, :626-628)
+        check(fn("fus_westervelt_mass", self.dtype)(
+            self.un.data_ptr(), self.ku.data_ptr(), self.c2.data_ptr(), self.c5.data_ptr(),
+            self.m.data_ptr(), self.b.data_ptr(), self.detJ.data_ptr(), self.dofmap.data_ptr(),
+            self.ncells, self.n**3, current_stream()), "fus_westervelt_mass")
+        # b += K(c3; un) + K(c4; vn) with ONE read of G                      (:620-625)
+        check(fn("fus_stiffness2", self.dtype)(
+            self.un.data_ptr(), self.c3.data_ptr(), self.ku.data_ptr(), self.c4.data_ptr(),
+            self.b.data_ptr(), self.G.data_ptr(), self.dofmap.data_ptr(), None, self.ncells, self.P,
+            FUS_TABLES_RESIDENT, current_stream()), "fus_stiffness2")
+        # b += g*src + dg*src2 + vn*absb                                      (:629-639)
+        self._boundary(stage, g, dg, use_table)
+
+    def _close(self, stage, dt, count_step):
+        last = stage == 3
+        check(fn("fus_rk_close_westervelt", self.dtype)(
+            self.u.data_ptr(), self.v.data_ptr(), self.u0.data_ptr(), self.v0.data_ptr(),
+            self.ku.data_ptr(), None, self.un.data_ptr(), self.b.data_ptr(), self.m.data_ptr(),
+            self.m0.data_ptr(), B_RUNGE[stage] * dt, 0.0 if last else A_RUNGE[stage + 1] * dt,
+            2 if last else 1, self.ndofs, self.step_dev.data_ptr() if count_step else None,
+            current_stream()), "fus_rk_close_westervelt")
+
+    def stage_bytes(self):
+        s = self.dtype.itemsize
+        Nd = self.n**3
+        return super().stage_bytes() + self.ncells * Nd * (4 + s) + 6 * s * self.ndofs
