@@ -1,0 +1,471 @@
+#!/usr/bin/env python
+"""bench.py - the headline benchmark of the hot path on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1], "demo_linear_box"): linear acoustic wave,
+explicit RK4, degree-4 hexahedra, 80^3 cells = 33 076 161 dofs per GPU, float64,
+source facets on x=0 and absorbing facets on x=L (cuda/demo_linear_box.py:53-122,
+256-263).  A *step* is one RK4 time step = 4 fused stages.  With N > 1 the box is
+block-partitioned, every GPU keeps an 80^3 block (weak scaling) and the ghost
+dofs are exchanged over NCCL each stage.
+
+The JSON line: ``value`` = fused-RK-stage throughput in GDoF/s (global dofs x 4
+stages x K / time), the metric BASELINE.json names ("operator GDoF/s and RK
+time-steps/s"); ``steps_per_s`` and the stand-alone operator GDoF/s ride along.
+``roofline`` is the stiffness kernel (the dominant kernel) against the measured
+HBM peak; ``cpu_baseline`` is the reference's CPU path (its own C++
+sum-factorisation templates when oracle/_ref is built, else the C port) timed on
+this host's cores on a bounded sample of the same workload.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# workload constants: cuda/demo_linear_box.py:53-66, 116
+P = 4
+F0, P0, C0, RHO = 0.5e6, 60000.0, 1500.0, 1000.0
+DOMAIN_LENGTH = 0.12
+N_PER_GPU = 80  # int(2 * 0.12 / (1500 / 0.5e6)) = 80 cells per direction
+CFL = 0.65
+CPU_SAMPLE_N = 24  # cells per direction of the bounded CPU sample (P=4: 912 673 dofs)
+
+
+def peaks():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cfl_dt(h):
+    dt = CFL * h / (C0 * P**2)
+    period = 1.0 / F0
+    return period / (int(period / dt) + 1)
+
+
+# --------------------------------------------------------------------------- #
+# clocks sampler (nvidia-smi during the timed region)
+# --------------------------------------------------------------------------- #
+
+
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [ln for ts, ln in self.lines if t0 - 0.05 <= ts <= t1 + 0.15] or [ln for _, ln in self.lines]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in rows:
+            f = [x.strip() for x in ln.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for nme, val in zip(names, f[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- #
+# problem set-up (device-side geometry; host substrate for mesh / dofmap)
+# --------------------------------------------------------------------------- #
+
+
+def build_problem(rank, world, n_per_gpu, dtype):
+    import torch
+
+    from fenicsx_fus_gpu_b200 import precompute as pre
+    from fenicsx_fus_gpu_b200 import substrate as S
+    from fenicsx_fus_gpu_b200 import utils
+    from fenicsx_fus_gpu_b200.scatterer import HaloExchange
+    from fenicsx_fus_gpu_b200.solver import LinearSpectral3D, linear_source
+
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    tb = S.element_tables(P, "basix", dtype)
+    grid = S.block_grid(world)
+    ncells = tuple(n_per_gpu * g for g in grid)
+    h = DOMAIN_LENGTH / N_PER_GPU  # the demo's cell size; the box grows with the rank grid
+    lengths = tuple(h * n for n in ncells)
+    halo = None
+    if world == 1:
+        mesh = S.create_box(ncells, lengths, dtype=dtype)
+        dofmap = S.tensor_dofmap(mesh, P)
+        ndofs = S.num_dofs(ncells, P)
+        nlocal = ndofs
+    else:
+        part = S.partition_box(ncells, P, world, lengths=lengths, dtype=dtype, ranks=[rank], grid=grid)[0]
+        mesh, dofmap = part.mesh, part.dofmap
+        nlocal = part.index_map.size_local
+        ndofs = nlocal + part.index_map.num_ghosts
+        od, gd = utils.compute_scatterer_data(part.index_map)
+        halo = HaloExchange(None, od, gd, nlocal, dtype)
+    nc = mesh.num_cells
+    nd3 = tb.n**3
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
+    x_dofs, x_g = d(mesh.x_dofs), d(mesh.x_g)
+    G = torch.empty((nc, nd3, 6), dtype=tdt, device="cuda")
+    detJ = torch.empty((nc, nd3), dtype=tdt, device="cuda")
+    pre.compute_geometry(G, detJ, (x_dofs, x_g), nc, d(tb.dphi), d(tb.wts))
+    bd1, bd2 = S.boundary_facets(mesh, 2), S.boundary_facets(mesh, 3)  # x=0 source, x=L absorbing
+    dJ1 = torch.empty((bd1.shape[0], tb.n**2), dtype=tdt, device="cuda")
+    dJ2 = torch.empty((bd2.shape[0], tb.n**2), dtype=tdt, device="cuda")
+    pre.compute_boundary_facets_scaled_jacobian_determinant(dJ1, (x_dofs, x_g), d(bd1), d(tb.dphi_f), d(tb.wts_f))
+    pre.compute_boundary_facets_scaled_jacobian_determinant(dJ2, (x_dofs, x_g), d(bd2), d(tb.dphi_f), d(tb.wts_f))
+    fd1 = S.facet_dofmap(dofmap, bd1, tb.local_facet_dof)
+    fd2 = S.facet_dofmap(dofmap, bd2, tb.local_facet_dof)
+    full = lambda n, v: torch.full((n,), v, dtype=tdt, device="cuda")  # noqa: E731
+    dofmap_d = d(dofmap)
+    solver = LinearSpectral3D(
+        P, dtype, ndofs, dofmap_d, G, detJ, tb.dphi_1D, full(nc, 1.0 / RHO / C0 / C0), full(nc, -1.0 / RHO),
+        fd1, dJ1, full(bd1.shape[0], 1.0 / RHO), fd2, dJ2, full(bd2.shape[0], -1.0 / RHO / C0),
+        halo=halo, source=lambda t: linear_source(t, F0, P0, C0))
+    info = dict(ncells_local=nc, ndofs_local=ndofs, nlocal=nlocal, global_cells=ncells,
+                global_dofs=S.num_dofs(ncells, P), grid=grid, h=h, detJ=detJ, tb=tb, dofmap=dofmap_d)
+    return solver, info
+
+
+# --------------------------------------------------------------------------- #
+# CPU arm: the reference's CPU path on a bounded sample
+# --------------------------------------------------------------------------- #
+
+
+class CpuRK:
+    """numba-cpu/demo_linear_box.py:425-459 with the reference operators
+    (oracle/_ref C++ templates, else the oracle C port), ``cores`` threads each
+    owning 1/k of the cells - the reference scales through MPI ranks only."""
+
+    def __init__(self, n, dtype, cores):
+        from fenicsx_fus_gpu_b200 import substrate as S
+        from oracle import oracle as orc
+
+        self.orc, self.cores, self.dtype = orc, cores, dtype
+        self.kind = "reference" if orc.ref_lib() is not None else "port"
+        tb = S.element_tables(P, "basix", dtype)
+        h = DOMAIN_LENGTH / N_PER_GPU
+        mesh = S.create_box(n, h * n, dtype=dtype)
+        self.dofmap = S.tensor_dofmap(mesh, P)
+        self.nd = S.num_dofs(n, P)
+        nc = mesh.num_cells
+        self.G = np.zeros((nc, tb.n**3, 6), dtype)
+        detJ = np.zeros((nc, tb.n**3), dtype)
+        orc.compute_scaled_geometrical_factor(self.G, (mesh.x_dofs, mesh.x_g), nc, tb.dphi, tb.wts)
+        orc.compute_scaled_jacobian_determinant(detJ, (mesh.x_dofs, mesh.x_g), nc, tb.dphi, tb.wts)
+        self.c2 = np.full(nc, -1.0 / RHO, dtype)
+        self.m = np.zeros(self.nd, dtype)
+        orc.mass_operator(np.ones(self.nd, dtype), np.full(nc, 1.0 / RHO / C0 / C0, dtype), self.m, detJ, self.dofmap)
+        bd1, bd2 = S.boundary_facets(mesh, 2), S.boundary_facets(mesh, 3)
+        self.fd1 = S.facet_dofmap(self.dofmap, bd1, tb.local_facet_dof)
+        self.fd2 = S.facet_dofmap(self.dofmap, bd2, tb.local_facet_dof)
+        self.dJ1 = np.zeros((bd1.shape[0], tb.n**2), dtype)
+        self.dJ2 = np.zeros((bd2.shape[0], tb.n**2), dtype)
+        orc.compute_boundary_facets_scaled_jacobian_determinant(self.dJ1, (mesh.x_dofs, mesh.x_g), bd1, tb.dphi_f, tb.wts_f)
+        orc.compute_boundary_facets_scaled_jacobian_determinant(self.dJ2, (mesh.x_dofs, mesh.x_g), bd2, tb.dphi_f, tb.wts_f)
+        self.fc1 = np.full(bd1.shape[0], 1.0 / RHO, dtype)
+        self.fc2 = np.full(bd2.shape[0], -1.0 / RHO / C0, dtype)
+        self.dphi = tb.dphi_1D
+        self.dt = cfl_dt(h)
+        z = lambda: np.zeros(self.nd, dtype)  # noqa: E731
+        self.u, self.v, self.u0, self.v0, self.un, self.vn = z(), z(), z(), z(), z(), z()
+        self.ku, self.kv, self.g, self.b = z(), z(), z(), z()
+        self.ybuf = np.zeros((cores, self.nd), dtype)
+        self.t = 0.0
+        self.sample = f"{n}^3 cells, degree {P}, {self.nd} dofs, {np.dtype(dtype).name}"
+
+    def step(self):
+        from fenicsx_fus_gpu_b200.solver import A_RUNGE, B_RUNGE, C_RUNGE, linear_source
+
+        o, dt = self.orc, self.dt
+        self.u0[:] = self.u
+        self.v0[:] = self.v
+        for i in range(4):
+            self.un[:] = self.u0
+            self.vn[:] = self.v0
+            o.axpy(A_RUNGE[i] * dt, self.ku, self.un)
+            o.axpy(A_RUNGE[i] * dt, self.kv, self.vn)
+            o.copy(self.vn, self.ku)
+            o.fill(linear_source(self.t + C_RUNGE[i] * dt, F0, P0, C0)[0], self.g)
+            o.fill(0.0, self.b)
+            self.ybuf[:] = 0
+            o.stiffness_ranks(P, self.un, self.c2, self.ybuf, self.G, self.dofmap, self.dphi, self.cores)
+            self.b += self.ybuf.sum(axis=0)
+            o.mass_operator(self.g, self.fc1, self.b, self.dJ1, self.fd1)
+            o.mass_operator(self.vn, self.fc2, self.b, self.dJ2, self.fd2)
+            o.pointwise_divide(self.b, self.m, self.kv)
+            o.axpy(B_RUNGE[i] * dt, self.ku, self.u)
+            o.axpy(B_RUNGE[i] * dt, self.kv, self.v)
+        self.t += dt
+
+
+def time_cpu(steps, warmup, budget_s=25.0):
+    cores = len(os.sched_getaffinity(0))
+    rk = CpuRK(CPU_SAMPLE_N, np.float64, cores)
+    for _ in range(max(1, warmup)):
+        rk.step()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        rk.step()
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    el = time.perf_counter() - t0
+    gd = rk.nd * 4 * done / el / 1e9
+    return dict(value=gd, unit="GDoF/s", cores=cores, kind=rk.kind,
+                sample=f"{done} RK4 steps on {rk.sample} ({el:.1f} s); stiffness on {cores} threads "
+                       f"each owning 1/{cores} of the cells (mpirun -n {cores} emulation, no halo cost)",
+                ms_per_step=el / done * 1e3, steps_per_s=done / el, steps=done)
+
+
+# --------------------------------------------------------------------------- #
+# main
+# --------------------------------------------------------------------------- #
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU, help="cells per direction per GPU (default: the demo's 80)")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(3, a.warmup)
+    config = {"workload": f"demo_linear_box: linear wave, RK4, degree {P} hexahedra, {a.n_per_gpu}^3 cells per GPU "
+                          f"(BASELINE.json configs[1]), {a.dtype}",
+              "degree": P, "cells_per_gpu": a.n_per_gpu**3, "parallelism": f"block partition x{world}, NCCL halo",
+              "l2": "working set per GPU ~6 GB >> 126 MB L2 (no flush needed)"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        r = time_cpu(a.steps, a.warmup)
+        line = {"impl": "reference", "metric": "fused RK4 stage throughput (global dofs x stages / s)",
+                "value": r["value"], "unit": "GDoF/s", "n_gpus": a.gpus, "steps": r["steps"], "warmup": max(1, a.warmup),
+                "ms_per_step": r["ms_per_step"], "steps_per_s": r["steps_per_s"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": "GDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this framework has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from fenicsx_fus_gpu_b200 import _lib
+    from fenicsx_fus_gpu_b200 import operators as ops
+
+    dtype = np.float64 if a.dtype == "f64" else np.float32
+    s = np.dtype(dtype).itemsize
+    solver, info = build_problem(rank, world, a.n_per_gpu, dtype)
+    dt = cfl_dt(info["h"])
+    lib = _lib.lib()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing: K graph-replayed RK4 steps ------------------
+    solver.init()
+    solver.rk4(0.0, dt, warmup)  # warm-up (captures the graph)
+    lib.fus_reset_launch_count()
+    barrier()
+    clocks = Clocks(local_rank)
+    clocks.start()
+    time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    barrier()
+    e0.record()
+    solver.rk4(solver.t, dt, a.steps)
+    e1.record()
+    barrier()
+    w1 = time.time()
+    elapsed = maxr(e0.elapsed_time(e1) * 1e-3)
+    clk = clocks.stop(w0, w1)
+    gdofs_global = info["global_dofs"]
+    value = gdofs_global * 4 * a.steps / elapsed / 1e9
+    # kernels per step: counted once in eager mode (a graph replay bypasses the C entry points)
+    lib.fus_reset_launch_count()
+    solver.use_graph = False
+    solver.rk4(solver.t, dt, 1)
+    torch.cuda.synchronize()
+    per_step = int(lib.fus_launch_count())
+    solver.use_graph = True
+
+    # ---- end to end: per step, H2D of the step's source amplitudes from pinned host,
+    #      the step, D2H of the sampled pressure plane (the demo's 100x100 probe grid) -------
+    nsample = min(10000, info["nlocal"])
+    sample_idx = torch.linspace(0, info["nlocal"] - 1, nsample, device="cuda").to(torch.int64)
+    sample_dev = torch.empty(nsample, dtype=solver.T, device="cuda")
+    sample_host = torch.empty(nsample, dtype=solver.T).pin_memory()
+    tab_host = torch.from_numpy(solver.source_table(solver.t, dt, a.steps + warmup)).pin_memory()
+    solver.gtab = torch.zeros((1, 8), dtype=solver.T, device="cuda")
+    solver.step_dev.zero_()
+    solver._capture(dt)  # graph bound to the 1-row device table
+    row = solver.gtab
+
+    def e2e_step(k):
+        row.copy_(tab_host[k:k + 1], non_blocking=True)  # H2D: this step's inputs
+        solver.step_dev.zero_()
+        solver.replay_step(dt)
+        check = _lib.fn("fus_pack_fwd", dtype)(solver.u.data_ptr(), sample_dev.data_ptr(), sample_idx.data_ptr(),
+                                               nsample, torch.cuda.current_stream().cuda_stream)
+        assert check == 0
+        sample_host.copy_(sample_dev, non_blocking=True)  # D2H: the step's result
+        torch.cuda.current_stream().synchronize()
+        return float(sample_host[0])
+
+    for k in range(warmup):
+        e2e_step(k)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for k in range(a.steps):
+        e2e_step(warmup + k)
+    e1.record()
+    barrier()
+    e2e_elapsed = maxr(max(e0.elapsed_time(e1) * 1e-3, 0.0))
+    e2e_wall = maxr(time.perf_counter() - t0)
+    e2e_value = gdofs_global * 4 * a.steps / max(e2e_elapsed, e2e_wall) / 1e9
+    h2d = 8 * s
+    d2h = nsample * s
+
+    # ---- the dominant kernel alone: stiffness launches under CUDA events (roofline) ----
+    nc, nd = info["ncells_local"], info["ndofs_local"]
+    n = P + 1
+    nd3 = n**3
+    K = ops.stiffness_operator(P, dtype)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(nd, dtype=solver.T, device="cuda", generator=gen)
+    y = torch.zeros(nd, dtype=solver.T, device="cuda")
+    D = torch.from_numpy(info["tb"].dphi_1D).cuda()
+    reps = max(20, a.steps)
+    for _ in range(3):
+        K[nc, (n, n, n)](x, solver.cell_coeff2, y, solver.G, solver.dofmap, D)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    barrier()
+    for ea, eb in evs:
+        y.zero_()
+        ea.record()
+        K[nc, (n, n, n)](x, solver.cell_coeff2, y, solver.G, solver.dofmap, D)
+        eb.record()
+    torch.cuda.synchronize()
+    t_stiff = float(np.mean([ea.elapsed_time(eb) for ea, eb in evs])) * 1e-3
+    bytes_stiff = nc * (nd3 * 4 + 6 * nd3 * s + s) + 2 * s * nd  # B_K per cell + 2s per dof
+    peak, peak_kind = peaks()
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "stiffness_traffic.json")))
+        if a.n_per_gpu == tr.get("n_per_gpu") and a.dtype == tr.get("dtype"):
+            traffic = tr["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"kernel": "stiffness_kernel<double,5> (fus_stiffness_f64)" if a.dtype == "f64" else "stiffness_kernel<float,5>",
+                "bound": "hbm", "achieved": bytes_stiff / t_stiff / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": bytes_stiff / t_stiff / 1e9 / peak, "traffic": traffic, "peak_kind": peak_kind,
+                "algorithmic_bytes_per_launch": bytes_stiff, "launch_ms": t_stiff * 1e3}
+    # the mass operator (cells) for the "operators" block
+    evm = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    c1 = torch.ones(nc, dtype=solver.T, device="cuda")
+    for ea, eb in evm:
+        y.zero_()
+        ea.record()
+        ops.mass_operator[1, 128](x, c1, y, info["detJ"], solver.dofmap)
+        eb.record()
+    torch.cuda.synchronize()
+    t_mass = float(np.mean([ea.elapsed_time(eb) for ea, eb in evm])) * 1e-3
+    stage_bytes = solver.stage_bytes()
+    stage_t = elapsed / (4 * a.steps)
+
+    line = {
+        "metric": "fused RK4 stage throughput (global dofs x stages / s)", "value": value, "unit": "GDoF/s",
+        "n_gpus": world, "steps": a.steps, "warmup": warmup, "ms_per_step": elapsed / a.steps * 1e3,
+        "steps_per_s": a.steps / elapsed, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": a.dtype, "data": "synthetic", "config": {**config, "global_dofs": gdofs_global,
+                                                          "global_cells": list(info["global_cells"])},
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": "GDoF/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps_per_s": a.steps / max(e2e_elapsed, e2e_wall)},
+        "gpu_launches": per_step * a.steps,
+        "roofline": roofline,
+        "stage_roofline": {"bound": "hbm", "achieved": stage_bytes / stage_t / 1e9, "peak": peak, "unit": "GB/s",
+                           "frac": stage_bytes / stage_t / 1e9 / peak,
+                           "algorithmic_bytes_per_stage": stage_bytes, "stage_ms": stage_t * 1e3},
+        "operators": {"stiffness_gdofs": info["ndofs_local"] / t_stiff / 1e9, "mass_gdofs": info["ndofs_local"] / t_mass / 1e9,
+                      "per_gpu_dofs": info["ndofs_local"]},
+    }
+    if rank == 0:
+        if world == 1 and not a.no_cpu:
+            r = time_cpu(3, 1, budget_s=20.0)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

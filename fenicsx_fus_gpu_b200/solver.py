@@ -125,6 +125,8 @@ class _RK4:
         self.nstep = 0
         self._graph = None
         self._graph_dt = None
+        self._graph_tab = None
+        self.graph_error = None
         self._opened = False
         self._bdofs = None
         self._src = self._src2 = self._absb = None
@@ -246,10 +248,10 @@ class _RK4:
         self.gtab = _dev(self.source_table(self.t, dt, nsteps), self.T)
         self.step_dev.zero_()
         if self.use_graph:
-            if self._graph is None or self._graph_dt != dt or self._graph_tab != self.gtab.data_ptr():
+            if self._graph_dt != dt or self._graph_tab != self.gtab.data_ptr():
                 self._capture(dt)
             for _ in range(nsteps):
-                self._graph.replay()
+                self.replay_step(dt)
         else:
             for k in range(nsteps):
                 self._enqueue_step(dt, 0.0, True)
@@ -268,6 +270,14 @@ class _RK4:
         self.nstep += 1
         return self.t
 
+    def replay_step(self, dt):
+        """One RK4 step reading the source table row ``step_dev`` points at: a
+        graph replay (or, when capture is unavailable, the same launches eagerly)."""
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._enqueue_step(dt, 0.0, True)
+
     def _capture(self, dt):
         torch = _torch()
         # warm up outside capture (lazy NCCL communicators, module loading)
@@ -278,11 +288,16 @@ class _RK4:
         for t, s in zip(self._state(), saved):
             t.copy_(s)
         self.step_dev.copy_(step0)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._enqueue_step(dt, 0.0, True)
-        self._graph, self._graph_dt, self._graph_tab = g, dt, self.gtab.data_ptr()
-        # capture does not execute: state is still the saved one
+        self._graph_dt, self._graph_tab = dt, self.gtab.data_ptr()
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue_step(dt, 0.0, True)
+            self._graph = g  # capture does not execute: state is still the saved one
+        except Exception as e:  # e.g. a transport that cannot be captured
+            self._graph = None
+            self.graph_error = repr(e)
+            torch.cuda.synchronize()
 
     def _state(self):
         return [self.u, self.v, self.u0, self.v0, self.ku, self.kv, self.un, self.b, self.m]

@@ -1,0 +1,226 @@
+"""GPU parity of the fused RK4 loops and the halo exchange.
+
+* linear loop against the fixture produced by the reference's own numba-cpu
+  kernels (tests/golden/linear_rk4_P3.npz) and against the oracle loop;
+* Westervelt loop against the oracle restatement of
+  cuda/demo_nonlinear_bowl.py:529-657;
+* the multi-rank path (block partition, index maps, forward/reverse halo,
+  ghost handling) with the ranks emulated by threads on one GPU, against the
+  single-rank oracle;
+* halo exchange against the reference-generated scatter fixtures.
+
+Tolerances: rel-L2 <= 1e-12 (float64), <= 1e-5 (float32) - BASELINE.json.
+"""
+
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def _linear_solver(d, dt_type, halo=None, **kw):
+    from fenicsx_fus_gpu_b200.solver import LinearSpectral3D, linear_source
+
+    return LinearSpectral3D(
+        d.P, dt_type, d.ndofs, d.dofmap, d.G, d.detJ, d.tb.dphi_1D, d.cell_coeff1, d.cell_coeff2,
+        d.bfacet_dofmap1, d.detJ_f1, d.facet_coeff1, d.bfacet_dofmap2, d.detJ_f2, d.facet_coeff2,
+        halo=halo, source=lambda t: linear_source(t, d.f0, d.p0, d.c0), **kw)
+
+
+def _oracle_linear(d, dt, nsteps, dt_type):
+    from oracle import oracle as orc
+
+    m = np.zeros(d.ndofs, dt_type)
+    orc.mass_operator(np.ones(d.ndofs, dt_type), d.cell_coeff1, m, d.detJ, d.dofmap)
+    prob = orc.LinearProblem(d.P, d.dofmap, d.G, d.tb.dphi_1D, d.cell_coeff2, m, d.bfacet_dofmap1,
+                             d.detJ_f1, d.facet_coeff1, d.bfacet_dofmap2, d.detJ_f2, d.facet_coeff2,
+                             d.f0, d.p0, d.c0)
+    u, v = np.zeros(d.ndofs, dt_type), np.zeros(d.ndofs, dt_type)
+    orc.linear_rk4(prob, u, v, 0.0, dt, nsteps)
+    return u, v
+
+
+def test_linear_rk4_vs_reference_golden(golden_dir):
+    """20 RK4 steps, every kernel of the stage, against the loop run with the
+    reference's unmodified numba-cpu operators."""
+    import problems
+    from fenicsx_fus_gpu_b200 import substrate as S
+
+    g = np.load(os.path.join(golden_dir, "linear_rk4_P3.npz"))
+    P = int(g["P"])
+    mesh = S.BoxMesh((3, 3, 3), g["x_dofs"], g["x_g"], (0, 0, 0), (3, 3, 3), (float(g["L"]),) * 3)
+    d = problems.linear_problem(P, 3, float(g["L"]), mesh=mesh, dofmap=g["dofmap"],
+                                ndofs=int(g["dofmap"].max()) + 1, rho=float(g["rho"]),
+                                c0=float(g["c0"]), f0=float(g["f0"]), p0=float(g["p0"]))
+    assert rel_l2(d.G, g["G"]) < 1e-12  # oracle geometry == reference geometry
+    d.G, d.detJ = g["G"], g["detJ"]
+    for use_graph in (True, False):
+        s = _linear_solver(d, np.float64, use_graph=use_graph)
+        assert rel_l2(s.m.cpu().numpy(), g["m"]) < 1e-13
+        s.init()
+        t = s.rk4(0.0, float(g["dt"]), int(g["nsteps"]))
+        assert abs(t - float(g["t_final"])) < 1e-18
+        assert rel_l2(s.u.cpu().numpy(), g["u"]) < 1e-12
+        assert rel_l2(s.v.cpu().numpy(), g["v"]) < 1e-12
+
+
+@pytest.mark.parametrize("P,N,tag,nsteps", [(4, 5, "f64", 12), (4, 5, "f32", 12), (2, 6, "f64", 10),
+                                            (6, 3, "f64", 8)])
+def test_linear_rk4_vs_oracle(P, N, tag, nsteps):
+    import problems
+
+    dtt = np.float64 if tag == "f64" else np.float32
+    L = 0.01
+    d = problems.linear_problem(P, N, L, dtt, perturb=0.12, seed=P)
+    dt = problems.cfl_dt(P, L / N, d.c0, d.f0)
+    u_ref, v_ref = _oracle_linear(d, dt, nsteps, dtt)
+    s = _linear_solver(d, dtt)
+    s.init()
+    s.rk4(0.0, dt, nsteps)
+    tol = 1e-12 if tag == "f64" else 1e-5
+    assert rel_l2(s.u.cpu().numpy(), u_ref) < tol
+    assert rel_l2(s.v.cpu().numpy(), v_ref) < tol
+    # eager stepping with host-evaluated source scalars gives the same answer
+    e = _linear_solver(d, dtt, use_graph=False)
+    e.init()
+    for _ in range(nsteps):
+        e.step_eager(dt)
+    assert rel_l2(e.u.cpu().numpy(), s.u.cpu().numpy()) < (1e-13 if tag == "f64" else 1e-6)
+    # continuing the same solver (second rk4 call) == one long run
+    s2 = _linear_solver(d, dtt)
+    s2.init()
+    s2.rk4(0.0, dt, nsteps // 2)
+    s2.rk4(s2.t, dt, nsteps - nsteps // 2)
+    assert rel_l2(s2.u.cpu().numpy(), s.u.cpu().numpy()) < (1e-13 if tag == "f64" else 1e-6)
+
+
+@pytest.mark.parametrize("P,N,tag", [(4, 4, "f64"), (3, 5, "f64"), (4, 4, "f32")])
+def test_westervelt_rk4_vs_oracle(P, N, tag):
+    import problems
+    from fenicsx_fus_gpu_b200.solver import WesterveltSpectral3D, westervelt_source
+    from oracle import oracle as orc
+
+    dtt = np.float64 if tag == "f64" else np.float32
+    L = 0.006
+    d = problems.westervelt_problem(P, N, L, dtt, perturb=0.1, seed=7)
+    dt = problems.cfl_dt(P, L / N, d.c0, d.f0, cfl=0.4)
+    nsteps = 10
+    ones = np.ones(d.ndofs, dtt)
+    m0 = np.zeros(d.ndofs, dtt)
+    orc.mass_operator(ones, d.cell_coeff1, m0, d.detJ, d.dofmap)
+    orc.mass_operator(ones, d.facet_coeff1_2, m0, d.detJ_f2, d.bfacet_dofmap2)
+    prob = orc.WesterveltProblem(d.P, d.dofmap, d.G, d.detJ, d.tb.dphi_1D, d.cell_coeff2, d.cell_coeff3,
+                                 d.cell_coeff4, d.cell_coeff5, m0, d.bfacet_dofmap1, d.detJ_f1,
+                                 d.facet_coeff1_1, d.facet_coeff2_1, d.bfacet_dofmap2, d.detJ_f2,
+                                 d.facet_coeff2_2, d.f0, d.p0, d.c0)
+    u_ref, v_ref = np.zeros(d.ndofs, dtt), np.zeros(d.ndofs, dtt)
+    orc.westervelt_rk4(prob, u_ref, v_ref, 0.0, dt, nsteps)
+    assert np.linalg.norm(u_ref) > 0
+
+    s = WesterveltSpectral3D(
+        d.P, dtt, d.ndofs, d.dofmap, d.G, d.detJ, d.tb.dphi_1D, d.cell_coeff1, d.cell_coeff2,
+        d.cell_coeff3, d.cell_coeff4, d.cell_coeff5, d.bfacet_dofmap1, d.detJ_f1, d.facet_coeff1_1,
+        d.facet_coeff2_1, d.bfacet_dofmap2, d.detJ_f2, d.facet_coeff1_2, d.facet_coeff2_2,
+        source=lambda t: westervelt_source(t, d.f0, d.p0, d.c0))
+    assert rel_l2(s.m0.cpu().numpy(), m0) < (1e-13 if tag == "f64" else 1e-6)
+    s.init()
+    s.rk4(0.0, dt, nsteps)
+    tol = 1e-12 if tag == "f64" else 1e-5
+    assert rel_l2(s.u.cpu().numpy(), u_ref) < tol
+    assert rel_l2(s.v.cpu().numpy(), v_ref) < tol
+
+
+@pytest.mark.parametrize("name", ["r2", "r3", "r8"])
+def test_halo_exchange_vs_reference_fixture(golden_dir, name):
+    """Forward and reverse halo through HaloExchange (ranks emulated by threads
+    on one GPU) against what numba-cpu/scatterer.py produced."""
+    from fenicsx_fus_gpu_b200.scatterer import HaloExchange, LocalCluster
+
+    with np.load(os.path.join(golden_dir, f"scatter_{name}.npz")) as z:
+        g = {k: z[k] for k in z.files}  # read everything before the rank threads start
+    R = int(g["nranks"])
+
+    def lists(r, which):
+        ranks = g[f"r{r}_{which}_ranks"]
+        return [[g[f"r{r}_{which}_idx{i}"] for i in range(ranks.size)], g[f"r{r}_{which}_size"], ranks]
+
+    def body(r, transport):
+        N = int(g[f"r{r}_size_local"])
+        halo = HaloExchange(transport, lists(r, "owners"), lists(r, "ghosts"), N, np.float64)
+        v = torch.from_numpy(g[f"r{r}_vec"]).cuda()
+        f = v.clone()
+        halo.forward(f)
+        rv = v.clone()
+        halo.reverse(rv)
+        # two vectors in one round == two rounds
+        a, b2 = v.clone(), (2.0 * v).clone()
+        halo.forward(a, b2)
+        torch.cuda.synchronize()
+        return f.cpu().numpy(), rv.cpu().numpy(), a.cpu().numpy(), b2.cpu().numpy()
+
+    out = LocalCluster(R).run(body)
+    for r in range(R):
+        f, rv, a, b2 = out[r]
+        assert np.array_equal(f, g[f"r{r}_fwd"])  # forward moves values: bit exact
+        assert rel_l2(rv, g[f"r{r}_rev"]) < 1e-15  # reverse adds: order of atomics may differ
+        assert np.array_equal(a, f)
+        N = int(g[f"r{r}_size_local"])
+        assert np.array_equal(b2[N:], 2.0 * f[N:])
+
+
+@pytest.mark.parametrize("R,N,P", [(2, (4, 3, 3), 3), (8, (4, 4, 4), 2), (4, (4, 4, 2), 4)])
+def test_linear_rk4_partitioned_vs_serial_oracle(R, N, P):
+    """The multi-GPU algorithm end to end on one GPU: R partitions, each with
+    its own solver + halo exchange, against the single-rank oracle run."""
+    import problems
+    from fenicsx_fus_gpu_b200 import substrate as S
+    from fenicsx_fus_gpu_b200 import utils
+    from fenicsx_fus_gpu_b200.scatterer import HaloExchange, LocalCluster
+
+    dtt = np.float64
+    L = (0.012, 0.01, 0.011)
+    nsteps = 8
+    serial = problems.linear_problem(P, N, L, dtt, perturb=0.1, seed=11)
+    h = min(L[i] / N[i] for i in range(3))
+    dt = problems.cfl_dt(P, h, serial.c0, serial.f0)
+    u_ref, v_ref = _oracle_linear(serial, dt, nsteps, dtt)
+
+    parts = S.partition_box(N, P, R, lengths=L, dtype=dtt, perturb=0.1, seed=11)
+    sdata = utils.compute_scatterer_data_all([p.index_map for p in parts])
+
+    def body(r, transport):
+        p = parts[r]
+        nd = p.index_map.size_local + p.index_map.num_ghosts
+        d = problems.linear_problem(P, None, None, dtt, mesh=p.mesh, dofmap=p.dofmap, ndofs=nd)
+        halo = HaloExchange(transport, sdata[r][0], sdata[r][1], p.index_map.size_local, dtt)
+        s = _linear_solver(d, dtt, halo=halo, use_graph=False)
+        s.init()
+        s.rk4(0.0, dt, nsteps)
+        torch.cuda.synchronize()
+        return s.u.cpu().numpy(), s.v.cpu().numpy()
+
+    out = LocalCluster(R).run(body)
+    u = np.zeros_like(u_ref)
+    v = np.zeros_like(v_ref)
+    for r, p in enumerate(parts):
+        nl = p.index_map.size_local
+        u[p.local_to_serial[:nl]] = out[r][0][:nl]
+        v[p.local_to_serial[:nl]] = out[r][1][:nl]
+    assert rel_l2(u, u_ref) < 1e-12
+    assert rel_l2(v, v_ref) < 1e-12
