@@ -245,7 +245,7 @@ class _RK4:
             self._open_first()
         if nsteps <= 0:
             return self.t
-        self.gtab = _dev(self.source_table(self.t, dt, nsteps), self.T)
+        self._load_table(self.source_table(self.t, dt, nsteps))
         self.step_dev.zero_()
         if self.use_graph:
             if self._graph_dt != dt or self._graph_tab != self.gtab.data_ptr():
@@ -259,6 +259,16 @@ class _RK4:
             self.t += dt
         self.nstep += nsteps
         return self.t
+
+    def _load_table(self, tab):
+        """Copy a host source table into the persistent device table (its address
+        is baked into the captured graph, so it only moves when it must grow)."""
+        torch = _torch()
+        rows = tab.shape[0]
+        if self.gtab is None or self.gtab.shape[0] < rows:
+            cap = max(rows, 256 if self.gtab is None else 2 * self.gtab.shape[0])
+            self.gtab = torch.zeros((cap, 8), dtype=self.T, device="cuda")
+        self.gtab[:rows].copy_(torch.from_numpy(np.ascontiguousarray(tab)))
 
     def step_eager(self, dt):
         """One step with host-evaluated source scalars (no table, no graph)."""
