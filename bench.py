@@ -289,7 +289,20 @@ def main():
     ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU, help="cells per direction per GPU (default: the demo's 80)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="launch the steps eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--watchdog", type=int, default=0, help="dump all Python stacks to stderr after this many seconds")
+    ap.add_argument("-v", "--verbose", action="store_true")
     a = ap.parse_args()
+    if a.watchdog > 0:
+        import faulthandler
+
+        faulthandler.dump_traceback_later(a.watchdog, exit=True)
+    t_start = time.time()
+
+    def log(msg):
+        if a.verbose:
+            print(f"[bench r{os.environ.get('RANK', '0')} +{time.time() - t_start:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -326,7 +339,10 @@ def main():
 
     dtype = np.float64 if a.dtype == "f64" else np.float32
     s = np.dtype(dtype).itemsize
+    log("building the problem")
     solver, info = build_problem(rank, world, a.n_per_gpu, dtype)
+    solver.use_graph = not a.no_graph
+    log(f"problem built: {info['ndofs_local']} local dofs, {info['ncells_local']} cells")
     dt = cfl_dt(info["h"])
     lib = _lib.lib()
 
@@ -346,6 +362,8 @@ def main():
     # ---- device-resident timing: K graph-replayed RK4 steps ------------------
     solver.init()
     solver.rk4(0.0, dt, warmup)  # warm-up (captures the graph)
+    torch.cuda.synchronize()
+    log(f"warm-up done (graph={'yes' if solver._graph is not None else 'no: ' + str(solver.graph_error)})")
     lib.fus_reset_launch_count()
     barrier()
     clocks = Clocks(local_rank)
@@ -365,11 +383,12 @@ def main():
     value = gdofs_global * 4 * a.steps / elapsed / 1e9
     # kernels per step: counted once in eager mode (a graph replay bypasses the C entry points)
     lib.fus_reset_launch_count()
+    log(f"timed region done: {elapsed * 1e3 / a.steps:.3f} ms/step")
     solver.use_graph = False
     solver.rk4(solver.t, dt, 1)
     torch.cuda.synchronize()
     per_step = int(lib.fus_launch_count())
-    solver.use_graph = True
+    solver.use_graph = not a.no_graph
 
     # ---- end to end: per step, H2D of the step's source amplitudes from pinned host,
     #      the step, D2H of the sampled pressure plane (the demo's 100x100 probe grid) -------
@@ -380,7 +399,9 @@ def main():
     tab_host = torch.from_numpy(solver.source_table(solver.t, dt, a.steps + warmup)).pin_memory()
     solver.gtab = torch.zeros((1, 8), dtype=solver.T, device="cuda")
     solver.step_dev.zero_()
-    solver._capture(dt)  # graph bound to the 1-row device table
+    if solver.use_graph:
+        solver._capture(dt)  # graph bound to the 1-row device table
+    log("e2e graph ready")
     row = solver.gtab
 
     def e2e_step(k):
@@ -409,6 +430,7 @@ def main():
     h2d = 8 * s
     d2h = nsample * s
 
+    log("e2e done")
     # ---- the dominant kernel alone: stiffness launches under CUDA events (roofline) ----
     nc, nd = info["ncells_local"], info["ndofs_local"]
     n = P + 1

@@ -583,20 +583,30 @@ def partition_box(
         bxo, ifx = touching(0, ox)
         byo, ify = touching(1, oy)
         bzo, ifz = touching(2, oz)
-        dest_lists = [[] for _ in range(nlocal)]
-        any_if = np.where(ifx | ify | ifz)[0]
-        for t in any_if:
-            xs = [bxo[t]] + ([bxo[t] + 1] if ifx[t] else [])
-            ys = [byo[t]] + ([byo[t] + 1] if ify[t] else [])
-            zs = [bzo[t]] + ([bzo[t] + 1] if ifz[t] else [])
-            dl = sorted(
-                rank_of(a, b, c) for a in xs for b in ys for c in zs
-                if rank_of(a, b, c) != rank
-            )
-            dest_lists[oloc[t]] = dl
-        counts = np.array([len(v) for v in dest_lists], dtype=np.int64)
+        # (owned dof, destination rank) pairs: the owner block plus one step
+        # along every axis on which the dof lies on an interface
+        pair_dof, pair_rank = [], []
+        for dx in (0, 1):
+            for dy in (0, 1):
+                for dz in (0, 1):
+                    if dx == dy == dz == 0:
+                        continue
+                    msk = (ifx if dx else True) & (ify if dy else True) & (ifz if dz else True)
+                    sel = np.nonzero(np.broadcast_to(msk, ox.shape))[0]
+                    if sel.size:
+                        pair_dof.append(oloc[sel])
+                        pair_rank.append(rank_of(bxo[sel] + dx, byo[sel] + dy, bzo[sel] + dz))
+        if pair_dof:
+            pd = np.concatenate(pair_dof)
+            pr = np.concatenate(pair_rank)
+            order = np.lexsort((pr, pd))  # by dof, destinations ascending
+            pd, pr = pd[order], pr[order]
+        else:
+            pd = np.zeros(0, np.int64)
+            pr = np.zeros(0, np.int64)
+        counts = np.bincount(pd, minlength=nlocal)
         d_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
-        d_arr = np.array([r for v in dest_lists for r in v], dtype=np.int32)
+        d_arr = pr.astype(np.int32)
         imap = IndexMap(
             nlocal, int(np.prod(G)), (int(offsets[rank]), int(offsets[rank + 1])),
             ghosts, ghost_owners, AdjacencyList(d_arr, d_off),

@@ -87,6 +87,25 @@ def main():
         elif op == "mass":
             f = lambda: ops.mass_operator[1, 128](x, c, y, detJ, dofmap)  # noqa: E731
             bytes_ = Nc * (Nd * (4 + s) + s) + 2 * s * nd
+        elif op == "close":
+            from fenicsx_fus_gpu_b200._lib import fn, current_stream
+            vs = [torch.randn(nd, dtype=tdt, device="cuda", generator=gen) for _ in range(8)]
+            m = torch.rand(nd, dtype=tdt, device="cuda", generator=gen) + 1.0
+            u_, v_, u0_, v0_, ku_, kv_, un_, b_ = vs
+            cl = fn("fus_rk_close", dt)
+            f = lambda: cl(u_.data_ptr(), v_.data_ptr(), u0_.data_ptr(), v0_.data_ptr(), ku_.data_ptr(), None,  # noqa: E731
+                           un_.data_ptr(), b_.data_ptr(), m.data_ptr(), 1e-9, 0.5e-9, 1, nd, None, current_stream())
+            bytes_ = 12 * s * nd
+        elif op == "copy":
+            a_ = torch.randn(nd * 4, dtype=tdt, device="cuda", generator=gen)
+            b_ = torch.empty_like(a_)
+            f = lambda: ops.copy[1, 1](a_, b_)  # noqa: E731
+            bytes_ = 2 * s * nd * 4
+        elif op == "torchcopy":
+            a_ = torch.randn(nd * 4, dtype=tdt, device="cuda", generator=gen)
+            b_ = torch.empty_like(a_)
+            f = lambda: b_.copy_(a_)  # noqa: E731
+            bytes_ = 2 * s * nd * 4
         else:
             continue
         mean, mn = time_op(f, a.reps)
