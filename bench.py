@@ -503,8 +503,15 @@ def main():
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Tear-down: ncclCommDestroy blocks while captured graphs still hold NCCL
+        # kernels, so drop the graphs first and do not wait on communicator
+        # destruction (the process is about to exit anyway).
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        solver._graph = None
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 
