@@ -103,7 +103,7 @@ __device__ __forceinline__ void open_body(const OpenArgs<T>& a, long long k) {
 }
 
 template <typename T, bool VEC>
-__global__ void __launch_bounds__(kThreads) rk_open_kernel(const OpenArgs<T> a) {
+__global__ void __launch_bounds__(kThreads, 4) rk_open_kernel(const OpenArgs<T> a) {
   constexpr int W = VEC ? Vec<T>::W : 1;
   const long long stride = (long long)gridDim.x * kThreads;
   const long long i0 = (long long)blockIdx.x * kThreads + threadIdx.x;
@@ -182,7 +182,7 @@ __device__ __forceinline__ void close_body(const CloseArgs<T>& a, long long k) {
 }
 
 template <typename T, bool VEC, bool WEST>
-__global__ void __launch_bounds__(kThreads) rk_close_kernel(const CloseArgs<T> a) {
+__global__ void __launch_bounds__(kThreads, 3) rk_close_kernel(const CloseArgs<T> a) {
   constexpr int W = VEC ? Vec<T>::W : 1;
   const long long stride = (long long)gridDim.x * kThreads;
   const long long i0 = (long long)blockIdx.x * kThreads + threadIdx.x;
