@@ -50,22 +50,42 @@ __global__ void __launch_bounds__(kThreads) vec_kernel(T alpha, const T* __restr
   long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
   if constexpr (VEC) {
     const long long nv = n / W;
-    for (long long k = i; k < nv; k += stride) {
-      T ra[W], rb[W], ro[W];
+    auto body = [&](long long k, T (&ra)[W], T (&rb)[W]) {
       if constexpr (OP != OP_FILL) *reinterpret_cast<V*>(ra) = reinterpret_cast<const V*>(a)[k];
       if constexpr (OP == OP_AXPY || OP == OP_DIV)
         *reinterpret_cast<V*>(rb) = reinterpret_cast<const V*>(b)[k];
+    };
+    auto finish = [&](long long k, T (&ra)[W], T (&rb)[W]) {
+      T ro[W];
 #pragma unroll
       for (int w = 0; w < W; ++w) ro[w] = apply<T, OP>(alpha, ra[w], rb[w]);
       reinterpret_cast<V*>(out)[k] = *reinterpret_cast<V*>(ro);
+    };
+    long long k = i;
+    // four independent 16-byte chunks per thread per trip: loads first, then stores
+    for (; k + 3 * stride < nv; k += 4 * stride) {
+      T a0[W], b0[W], a1[W], b1[W], a2[W], b2[W], a3[W], b3[W];
+      body(k, a0, b0);
+      body(k + stride, a1, b1);
+      body(k + 2 * stride, a2, b2);
+      body(k + 3 * stride, a3, b3);
+      finish(k, a0, b0);
+      finish(k + stride, a1, b1);
+      finish(k + 2 * stride, a2, b2);
+      finish(k + 3 * stride, a3, b3);
+    }
+    for (; k < nv; k += stride) {
+      T a0[W], b0[W];
+      body(k, a0, b0);
+      finish(k, a0, b0);
     }
     // tail
-    const long long k = nv * W + i;
-    if (k < n) {
+    const long long kt = nv * W + i;
+    if (kt < n) {
       T va = T(0), vb = T(0);
-      if constexpr (OP != OP_FILL) va = a[k];
-      if constexpr (OP == OP_AXPY || OP == OP_DIV) vb = b[k];
-      out[k] = apply<T, OP>(alpha, va, vb);
+      if constexpr (OP != OP_FILL) va = a[kt];
+      if constexpr (OP == OP_AXPY || OP == OP_DIV) vb = b[kt];
+      out[kt] = apply<T, OP>(alpha, va, vb);
     }
   } else {
     for (long long k = i; k < n; k += stride) {
