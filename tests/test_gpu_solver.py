@@ -224,3 +224,84 @@ def test_linear_rk4_partitioned_vs_serial_oracle(R, N, P):
         v[p.local_to_serial[:nl]] = out[r][1][:nl]
     assert rel_l2(u, u_ref) < 1e-12
     assert rel_l2(v, v_ref) < 1e-12
+
+
+def test_problem_builder_piston_vs_oracle():
+    """problem.box_setup / linear_solver (device geometry, facet groups filtered by a
+    centroid predicate - the piston demo's set-up) against the oracle loop on the same
+    arrays built on the host."""
+    import problems
+    from fenicsx_fus_gpu_b200 import problem
+    from fenicsx_fus_gpu_b200 import substrate as S
+    from oracle import oracle as orc
+
+    P, N, L, dtt, nsteps = 3, (4, 4, 3), (0.008, 0.008, 0.006), np.float64, 6
+    su = problem.box_setup(P, N, L, dtt, perturb=0.08, seed=4)
+    piston = problem.disc(0, 1, (0.004, 0.004), 0.0025)
+    keep = lambda cen: ~(piston(cen) & (cen[:, 2] < 0.0005))  # noqa: E731
+    s = problem.linear_solver(su, [0], [0, 1, 2, 3, 4, 5], source_predicate=piston, absorbing_predicate=keep)
+    # device geometry == oracle geometry
+    d = problems.linear_problem(P, N, L, dtt, perturb=0.08, seed=4)
+    assert rel_l2(su.dev["G"].cpu().numpy(), d.G) < 1e-12
+    assert rel_l2(su.dev["detJ"].cpu().numpy(), d.detJ) < 1e-13
+    # host-side facet groups for the oracle
+    tb = d.tb
+    bd1 = S.boundary_facets(d.mesh, 0, piston)
+    bd2 = np.concatenate([S.boundary_facets(d.mesh, f, keep) for f in range(6)])
+    assert 0 < bd1.shape[0] < N[0] * N[1]
+    assert bd2.shape[0] == 2 * (N[0] * N[1] + N[1] * N[2] + N[0] * N[2]) - bd1.shape[0]
+
+    def grp(bd):
+        dJ = np.zeros((bd.shape[0], tb.n**2))
+        orc.compute_boundary_facets_scaled_jacobian_determinant(dJ, (d.mesh.x_dofs, d.mesh.x_g), bd, tb.dphi_f, tb.wts_f)
+        return S.facet_dofmap(d.dofmap, bd, tb.local_facet_dof), dJ
+
+    d.bfacet_dofmap1, d.detJ_f1 = grp(bd1)
+    d.bfacet_dofmap2, d.detJ_f2 = grp(bd2)
+    d.facet_coeff1 = np.full(bd1.shape[0], 1.0 / d.rho)
+    d.facet_coeff2 = np.full(bd2.shape[0], -1.0 / d.rho / d.c0)
+    dt = problem.cfl_time_step(P, su.h, d.c0, d.f0, 0.65)
+    u_ref, v_ref = _oracle_linear(d, dt, nsteps, dtt)
+    s.init()
+    s.rk4(0.0, dt, nsteps)
+    assert rel_l2(s.u.cpu().numpy(), u_ref) < 1e-12
+    assert rel_l2(s.v.cpu().numpy(), v_ref) < 1e-12
+
+
+def test_full_size_properties_demo_linear_box():
+    """BASELINE.json configs[1] at full size (80^3 cells, degree 4, 33 M dofs, f64),
+    where the CPU oracle would need minutes: size-independent properties.
+    K 1 = 0, sum(M 1) = |Omega|, v.Ku = u.Kv, and the fused step conserves the
+    state when there is no source (u = v = 0 stays 0)."""
+    from fenicsx_fus_gpu_b200 import operators as ops
+    from fenicsx_fus_gpu_b200 import problem
+
+    P, N, L = 4, 80, 0.12
+    su = problem.box_setup(P, N, L, np.float64)
+    nd, nc = su.ndofs, su.mesh.num_cells
+    assert nd == 33076161
+    dm, G, dJ = su.dev["dofmap"], su.dev["G"], su.dev["detJ"]
+    D = torch.from_numpy(su.tables.dphi_1D).cuda()
+    c = torch.ones(nc, dtype=torch.float64, device="cuda")
+    K = ops.stiffness_operator(P, np.float64)
+
+    def apply(x):
+        y = torch.zeros(nd, dtype=torch.float64, device="cuda")
+        K[nc, (5, 5, 5)](x, c, y, G, dm, D)
+        return y
+
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    u = torch.randn(nd, dtype=torch.float64, device="cuda", generator=gen)
+    v = torch.randn(nd, dtype=torch.float64, device="cuda", generator=gen)
+    Ku, Kv = apply(u), apply(v)
+    ones = torch.ones(nd, dtype=torch.float64, device="cuda")
+    assert float(apply(ones).norm() / Ku.norm()) < 1e-12
+    assert abs(float(v @ Ku - u @ Kv)) / abs(float(v @ Ku)) < 1e-10
+    m = torch.zeros(nd, dtype=torch.float64, device="cuda")
+    ops.mass_operator[1, 128](ones, c, m, dJ, dm)
+    assert abs(float(m.sum()) - L**3) / L**3 < 1e-12
+    assert float(m.min()) > 0
+    s = problem.linear_solver(su, [2], [3], p0=0.0)
+    s.init()
+    s.rk4(0.0, 1e-8, 2)
+    assert float(s.u.abs().max()) == 0.0 and float(s.v.abs().max()) == 0.0
