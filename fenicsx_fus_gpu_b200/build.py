@@ -20,6 +20,7 @@ OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libfus_b200.so")
 SOURCES = ["api.cu", "stiffness.cu", "mass.cu", "vector.cu", "rk.cu", "geometry.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+EXTRA = os.environ.get("FUS_NVCC_EXTRA", "").split()  # experiments, e.g. -DFUS_CFG_ALT
 # IEEE division / sqrt (no fast-math): parity with the reference is rel-L2 <= 1e-12 in f64
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -51,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         s, obj = job
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, s), "-o", obj]
+        cmd = [NVCC, *FLAGS, *EXTRA, "-c", os.path.join(CSRC, s), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -66,16 +66,17 @@ struct Cfg;
     static constexpr int THREADS = THREADS_;            \
     static constexpr int MINB = MINB_;                  \
   };
+// (measured on B200, tools/sweep.py: 256-thread CTAs only pay where n^2 packs badly into 128)
 FUS_CFG(double, 3, 14, 128, 4)
 FUS_CFG(double, 4, 8, 128, 3)
 FUS_CFG(double, 5, 5, 128, 3)
 FUS_CFG(double, 6, 3, 128, 3)
-FUS_CFG(double, 7, 2, 128, 2)
+FUS_CFG(double, 7, 5, 256, 1)
 FUS_CFG(double, 8, 1, 64, 3)
 FUS_CFG(float, 3, 14, 128, 6)
 FUS_CFG(float, 4, 8, 128, 6)
 FUS_CFG(float, 5, 5, 128, 5)
-FUS_CFG(float, 6, 3, 128, 5)
+FUS_CFG(float, 6, 7, 256, 2)
 FUS_CFG(float, 7, 2, 128, 4)
 FUS_CFG(float, 8, 2, 128, 3)
 #undef FUS_CFG
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
   constexpr int N2 = L::N2;
   constexpr int THREADS = Cfg<T, n>::THREADS;
   static_assert(B * N2 <= THREADS, "one thread per (cell, j, k)");
+  static_assert(B <= 32, "one lane of warp 0 per bulk copy");
 
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -187,27 +189,24 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
     return (unsigned)((reinterpret_cast<unsigned long long>(a.G) + (unsigned long long)b * B * L::CB) & 15ull);
   };
 
+  // Called by all 32 lanes of warp 0: lane c issues the copy of cell c (B <= 14),
+  // so the B bulk copies of a batch go out in parallel instead of one after another.
   auto issue = [&](long long b, int s) {
     fence_proxy_async_smem();  // generic reads of this stage (previous use) before the refill
     const unsigned long long g0 =
         reinterpret_cast<unsigned long long>(a.G) + (unsigned long long)b * B * L::CB;
     const unsigned shift = (unsigned)(g0 & 15ull);
     unsigned char* st = stages + s * L::STAGE;
-    unsigned total = 0;
-#pragma unroll
-    for (int c = 0; c < B; ++c) {
-      const unsigned long long src = g0 + (unsigned long long)c * L::CB;
-      total += (unsigned)(((src + L::CB + 15ull) & ~15ull) - (src & ~15ull));
-    }
-    mbar_arrive_expect_tx(&full[s], total);
-    const uint64_t pol = l2_policy_evict_first();
-#pragma unroll
-    for (int c = 0; c < B; ++c) {
-      const unsigned long long src = g0 + (unsigned long long)c * L::CB;
-      const unsigned long long sa = src & ~15ull, se = (src + L::CB + 15ull) & ~15ull;
+    const int c = tid;
+    const unsigned long long src = g0 + (unsigned long long)c * L::CB;
+    const unsigned long long sa = src & ~15ull, se = (src + L::CB + 15ull) & ~15ull;
+    const unsigned bytes = c < B ? (unsigned)(se - sa) : 0u;
+    const unsigned total = __reduce_add_sync(0xffffffffu, bytes);
+    if (c == 0) mbar_arrive_expect_tx(&full[s], total);
+    __syncwarp();
+    if (c < B)
       bulk_g2s_hint(st + shift + c * L::GC - (unsigned)(src & 15ull), reinterpret_cast<const void*>(sa),
-                    (uint32_t)(se - sa), &full[s], pol);
-    }
+                    bytes, &full[s], l2_policy_evict_first());
   };
 
   // ---- register prefetch of the dofmap / x pencil of a batch ----------------
@@ -246,7 +245,7 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
   (void)xwn;
 
   // prologue: first batch of this CTA
-  if (tid == 0 && (long long)blockIdx.x < nb && bulk_eligible(blockIdx.x)) issue(blockIdx.x, 0);
+  if (tid < 32 && (long long)blockIdx.x < nb && bulk_eligible(blockIdx.x)) issue(blockIdx.x, 0);
   load_dofs(blockIdx.x, dof);
   load_dofs(blockIdx.x + stride, dofn);
   load_x(dof, xv, xw);
@@ -256,7 +255,7 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
     const int s = it & 1;
     const long long bn = b + stride;
     // TMA prefetch of the next batch into the other stage (consumed last iteration)
-    if (tid == 0 && bn < nb && bulk_eligible(bn)) issue(bn, s ^ 1);
+    if (tid < 32 && bn < nb && bulk_eligible(bn)) issue(bn, s ^ 1);
 
     unsigned char* st = stages + s * L::STAGE;
     const long long cell0 = b * B;
