@@ -28,6 +28,7 @@ def _sigs():
         "fus_set_dphi": [I, P, P],
         "fus_stiffness": [P, P, P, P, P, P, L, I, I, P],
         "fus_stiffness2": [P, P, P, P, P, P, P, P, L, I, I, P],
+        "fus_stiffness_westervelt": [P, P, P, P, P, P, P, P, P, P, P, P, L, I, I, P],
         "fus_mass": [P, P, P, P, P, L, I, P],
         "fus_axpy": [T, P, P, L, P],
         "fus_copy": [P, P, L, P],

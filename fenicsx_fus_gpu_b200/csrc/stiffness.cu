@@ -118,6 +118,11 @@ struct StiffArgs {
   T* y;
   const T* G;
   const int32_t* dofmap;
+  // Westervelt mode only
+  const T* detJ;
+  const T* cm;
+  const T* cy;
+  T* m;
   long long ncells;
   int bulk_ok;  // G base aligned for the 2-element vector loads of the AoS records
 };
@@ -141,9 +146,14 @@ __device__ __forceinline__ G6<float> load_g6(const float* p) {
   return {a.x, a.y, b.x, b.y, c.x, c.y};
 }
 
-template <typename T, int n, bool DUAL, bool ATOMIC>
+// MODE 0: y += K(ca; xa).  MODE 1: y += K(ca; xa) + K(cb; xb) with one read of G.
+// MODE 2: MODE 1 plus the Westervelt cell-mass pair on the same gathered pencils:
+//         m += M(cm; xa),  y += M(cy; xb^2)   (cuda/demo_nonlinear_bowl.py:609-612, 626-628)
+template <typename T, int n, int MODE, bool ATOMIC>
 __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
     stiffness_kernel(const StiffArgs<T> a) {
+  constexpr bool DUAL = MODE >= 1;
+  constexpr bool WEST = MODE == 2;
   using L = Layout<T, n>;
   using D = DTable<T, n - 1>;
   constexpr int B = L::B;
@@ -233,6 +243,18 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
     }
   };
 
+  auto load_detj = [&](long long b, T (&dj)[n]) {
+    const long long cell = b * B + cs;
+    if (lane_ok && b < nb && cell < a.ncells) {
+      const T* p = a.detJ + cell * (long long)Nd + t2;
+#pragma unroll
+      for (int i = 0; i < n; ++i) dj[i] = __ldg(p + i * N2);
+    } else {
+#pragma unroll
+      for (int i = 0; i < n; ++i) dj[i] = T(0);
+    }
+  };
+
   // Register pipeline, two batches deep so that no load depends on another load
   // issued in the same batch (the compiler is free to hoist these read-only
   // loads to the top of the loop body):
@@ -243,12 +265,17 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
   T xv[n], xw[n], xvn[n], xwn[n];  // xw*: second vector in dual mode
   (void)xw;
   (void)xwn;
+  T dj[WEST ? n : 1], djn[WEST ? n : 1], bex[WEST ? n : 1];  // Westervelt: detJ pencil, extra b term
+  (void)dj;
+  (void)djn;
+  (void)bex;
 
   // prologue: first batch of this CTA
   if (tid < 32 && (long long)blockIdx.x < nb && bulk_eligible(blockIdx.x)) issue(blockIdx.x, 0);
   load_dofs(blockIdx.x, dof);
   load_dofs(blockIdx.x + stride, dofn);
   load_x(dof, xv, xw);
+  if constexpr (WEST) load_detj(blockIdx.x, reinterpret_cast<T(&)[n]>(dj));
 
   int it = 0;
   for (long long b = blockIdx.x; b < nb; b += stride, ++it) {
@@ -277,6 +304,7 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
     // next and the x pencil of the next batch (its entries arrived a batch ago)
     load_dofs(bn + stride, dofm);
     load_x(dofn, xvn, xwn);
+    if constexpr (WEST) load_detj(bn, reinterpret_cast<T(&)[n]>(djn));
 
     // ---- x pencil (registers) -> tiles; x-direction gradient ----------------
     T gx[n];
@@ -284,6 +312,14 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
     if (active) {
       if constexpr (DUAL) {
         const T ca = a.ca[cell0 + cs], cb = a.cb[cell0 + cs];
+        if constexpr (WEST) {
+          const T cm = a.cm[cell0 + cs], cy = a.cy[cell0 + cs];
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            atomicAdd(a.m + dof[i], xv[i] * dj[i] * cm);   // m += cm detJ un
+            bex[i] = (xw[i] * xw[i]) * dj[i] * cy;          // b += cy detJ vn^2 (joins the scatter)
+          }
+        }
 #pragma unroll
         for (int i = 0; i < n; ++i) xv[i] = ca * xv[i] + cb * xw[i];
       } else {
@@ -342,7 +378,13 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
     if (active) {
       const T* Gc = Gs + cs * (L::GC / L::S) + t2 * 6;
 #pragma unroll
-      for (int l = 0; l < n; ++l) ry[l] = T(0);
+      for (int l = 0; l < n; ++l) {
+        if constexpr (WEST) {
+          ry[l] = bex[l];
+        } else {
+          ry[l] = T(0);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < n; ++i) {
         const T wy = uy1[i * L::SPY];
@@ -401,15 +443,16 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
       dofn[i] = dofm[i];
       xv[i] = xvn[i];
       if constexpr (DUAL) xw[i] = xwn[i];
+      if constexpr (WEST) dj[i] = djn[i];
     }
     __syncthreads();  // tiles and stage s are free again
   }
 }
 
-template <typename T, int n, bool DUAL, bool ATOMIC>
+template <typename T, int n, int MODE, bool ATOMIC>
 int launch_cfg(const StiffArgs<T>& a, cudaStream_t stream) {
   using L = Layout<T, n>;
-  auto kern = stiffness_kernel<T, n, DUAL, ATOMIC>;
+  auto kern = stiffness_kernel<T, n, MODE, ATOMIC>;
   static int blocks_per_sm = 0;  // per instantiation
   if (blocks_per_sm == 0) {
     FUS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM));
@@ -425,13 +468,13 @@ int launch_cfg(const StiffArgs<T>& a, cudaStream_t stream) {
   return 0;
 }
 
-template <typename T, bool DUAL>
+template <typename T, int MODE>
 int launch(const StiffArgs<T>& a, int P, int flags, cudaStream_t stream) {
   const bool atomic = !(flags & FUS_NO_ATOMICS);
 #define FUS_CASE(N)                                                       \
   case N - 1:                                                             \
-    return atomic ? launch_cfg<T, N, DUAL, true>(a, stream)               \
-                  : launch_cfg<T, N, DUAL, false>(a, stream);
+    return atomic ? launch_cfg<T, N, MODE, true>(a, stream)               \
+                  : launch_cfg<T, N, MODE == 2 ? 1 : MODE, false>(a, stream);
   switch (P) {
     FUS_CASE(3)
     FUS_CASE(4)
@@ -461,7 +504,8 @@ int set_dphi(int P, const T* dphi, cudaStream_t stream) {
 template <typename T>
 int stiffness_entry(const T* xa, const T* ca, const T* xb, const T* cb, T* y, const T* G,
                     const int32_t* dofmap, const T* dphi, int64_t ncells, int P, int flags,
-                    void* stream, bool dual) {
+                    void* stream, int mode, const T* detJ = nullptr, const T* cm = nullptr,
+                    const T* cy = nullptr, T* m = nullptr) {
   if (ncells < 0) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "stiffness: ncells < 0");
   if (P < 2 || P > 7) return fus_set_error(FUS_ERR_BAD_DEGREE, "stiffness: degree must be 2..7");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -478,9 +522,18 @@ int stiffness_entry(const T* xa, const T* ca, const T* xb, const T* cb, T* y, co
   a.y = y;
   a.G = G;
   a.dofmap = dofmap;
+  a.detJ = detJ;
+  a.cm = cm;
+  a.cy = cy;
+  a.m = m;
   a.ncells = ncells;
   a.bulk_ok = (reinterpret_cast<uintptr_t>(G) & (2 * sizeof(T) - 1)) == 0;  // 16-byte record loads
-  return dual ? launch<T, true>(a, P, flags, st) : launch<T, false>(a, P, flags, st);
+  if (mode == 2) {
+    if (flags & FUS_NO_ATOMICS)
+      return fus_set_error(FUS_ERR_BAD_ARGUMENT, "stiffness_westervelt: FUS_NO_ATOMICS not supported");
+    return launch<T, 2>(a, P, flags, st);
+  }
+  return mode == 1 ? launch<T, 1>(a, P, flags, st) : launch<T, 0>(a, P, flags, st);
 }
 
 }  // namespace
@@ -498,23 +551,39 @@ int fus_stiffness_f64(const double* x, const double* coeff, double* y, const dou
                       const int32_t* dofmap, const double* dphi, int64_t ncells, int P, int flags,
                       void* stream) {
   return stiffness_entry<double>(x, coeff, nullptr, nullptr, y, G, dofmap, dphi, ncells, P, flags,
-                                 stream, false);
+                                 stream, 0);
 }
 int fus_stiffness_f32(const float* x, const float* coeff, float* y, const float* G,
                       const int32_t* dofmap, const float* dphi, int64_t ncells, int P, int flags,
                       void* stream) {
   return stiffness_entry<float>(x, coeff, nullptr, nullptr, y, G, dofmap, dphi, ncells, P, flags,
-                                stream, false);
+                                stream, 0);
 }
 int fus_stiffness2_f64(const double* xa, const double* ca, const double* xb, const double* cb,
                        double* y, const double* G, const int32_t* dofmap, const double* dphi,
                        int64_t ncells, int P, int flags, void* stream) {
-  return stiffness_entry<double>(xa, ca, xb, cb, y, G, dofmap, dphi, ncells, P, flags, stream, true);
+  return stiffness_entry<double>(xa, ca, xb, cb, y, G, dofmap, dphi, ncells, P, flags, stream, 1);
 }
 int fus_stiffness2_f32(const float* xa, const float* ca, const float* xb, const float* cb, float* y,
                        const float* G, const int32_t* dofmap, const float* dphi, int64_t ncells,
                        int P, int flags, void* stream) {
-  return stiffness_entry<float>(xa, ca, xb, cb, y, G, dofmap, dphi, ncells, P, flags, stream, true);
+  return stiffness_entry<float>(xa, ca, xb, cb, y, G, dofmap, dphi, ncells, P, flags, stream, 1);
+}
+
+int fus_stiffness_westervelt_f64(const double* un, const double* c3, const double* vn,
+                                 const double* c4, const double* c2, const double* c5, double* m,
+                                 double* b, const double* G, const double* detJ,
+                                 const int32_t* dofmap, const double* dphi, int64_t ncells, int P,
+                                 int flags, void* stream) {
+  return stiffness_entry<double>(un, c3, vn, c4, b, G, dofmap, dphi, ncells, P, flags, stream, 2, detJ,
+                                 c2, c5, m);
+}
+int fus_stiffness_westervelt_f32(const float* un, const float* c3, const float* vn, const float* c4,
+                                 const float* c2, const float* c5, float* m, float* b,
+                                 const float* G, const float* detJ, const int32_t* dofmap,
+                                 const float* dphi, int64_t ncells, int P, int flags, void* stream) {
+  return stiffness_entry<float>(un, c3, vn, c4, b, G, dofmap, dphi, ncells, P, flags, stream, 2, detJ,
+                                c2, c5, m);
 }
 
 int fus_stiffness_host_f64(const double* x_host, double* y_host, int64_t nd, double* x_dev,

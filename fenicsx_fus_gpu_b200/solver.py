@@ -425,16 +425,13 @@ class WesterveltSpectral3D(_RK4):
         return super()._state() + [self.m0]
 
     def _assemble(self, stage, g, dg, use_table):
-        # m += M(c2; un)   and   b += M(c5; vn^2)   sharing detJ / dofmap   (:609-612, :626-628)
-        check(fn("fus_westervelt_mass", self.dtype)(
-            self.un.data_ptr(), self.ku.data_ptr(), self.c2.data_ptr(), self.c5.data_ptr(),
-            self.m.data_ptr(), self.b.data_ptr(), self.detJ.data_ptr(), self.dofmap.data_ptr(),
-            self.ncells, self.n**3, current_stream()), "fus_westervelt_mass")
-        # b += K(c3; un) + K(c4; vn) with ONE read of G                      (:620-625)
-        check(fn("fus_stiffness2", self.dtype)(
+        # b += K(c3; un) + K(c4; vn) + M(c5; vn^2) and m += M(c2; un): ONE pass over G, detJ
+        # and the dofmap, un / vn gathered once                    (:609-612, :620-628)
+        check(fn("fus_stiffness_westervelt", self.dtype)(
             self.un.data_ptr(), self.c3.data_ptr(), self.ku.data_ptr(), self.c4.data_ptr(),
-            self.b.data_ptr(), self.G.data_ptr(), self.dofmap.data_ptr(), None, self.ncells, self.P,
-            FUS_TABLES_RESIDENT, current_stream()), "fus_stiffness2")
+            self.c2.data_ptr(), self.c5.data_ptr(), self.m.data_ptr(), self.b.data_ptr(),
+            self.G.data_ptr(), self.detJ.data_ptr(), self.dofmap.data_ptr(), None, self.ncells, self.P,
+            FUS_TABLES_RESIDENT, current_stream()), "fus_stiffness_westervelt")
         # b += g*src + dg*src2 + vn*absb                                      (:629-639)
         self._boundary(stage, g, dg, use_table)
 

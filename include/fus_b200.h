@@ -86,6 +86,20 @@ int fus_stiffness2_f32(const float* xa, const float* coeff_a, const float* xb,
                        const float* coeff_b, float* y, const float* G, const int32_t* dofmap,
                        const float* dphi, int64_t ncells, int P, int flags, void* stream);
 
+/* The whole cell work of one Westervelt stage in ONE pass over G, detJ and the
+ * dofmap (cuda/demo_nonlinear_bowl.py:609-612 and 620-628):
+ *   b += K(c3 ; un) + K(c4 ; vn) + M(c5 ; vn^2)        m += M(c2 ; un)
+ * with M(c ; w)[dm] = c * detJ * w[dm].  un and vn are gathered once. */
+int fus_stiffness_westervelt_f64(const double* un, const double* c3, const double* vn,
+                                 const double* c4, const double* c2, const double* c5, double* m,
+                                 double* b, const double* G, const double* detJ,
+                                 const int32_t* dofmap, const double* dphi, int64_t ncells, int P,
+                                 int flags, void* stream);
+int fus_stiffness_westervelt_f32(const float* un, const float* c3, const float* vn, const float* c4,
+                                 const float* c2, const float* c5, float* m, float* b,
+                                 const float* G, const float* detJ, const int32_t* dofmap,
+                                 const float* dphi, int64_t ncells, int P, int flags, void* stream);
+
 /* Mass (diagonal) action on cells or boundary facets
  *   y[dm[e,i]] += x[dm[e,i]] * detJ[e,i] * coeff[e]
  * Replaces `mass_operator[grid, block](x, coeff, y, detJ, dofmap)` -

@@ -96,6 +96,19 @@ def main():
             f = lambda: cl(u_.data_ptr(), v_.data_ptr(), u0_.data_ptr(), v0_.data_ptr(), ku_.data_ptr(), None,  # noqa: E731
                            un_.data_ptr(), b_.data_ptr(), m.data_ptr(), 1e-9, 0.5e-9, 1, nd, None, current_stream())
             bytes_ = 12 * s * nd
+        elif op in ("wstage", "lstage"):
+            from fenicsx_fus_gpu_b200 import problem
+            su = problem.box_setup(P, N, 0.0015 * N, dt)
+            if op == "wstage":
+                sol = problem.westervelt_solver(su, [2], [0, 1, 2, 3, 4, 5], p0=1e5)
+                dtm = problem.cfl_time_step(P, su.h, 1480.0, 1.1e6, 0.4)
+            else:
+                sol = problem.linear_solver(su, [2], [3])
+                dtm = problem.cfl_time_step(P, su.h, 1500.0, 0.5e6, 0.65)
+            sol.init()
+            sol.rk4(0.0, dtm, 3)
+            f = lambda: sol.rk4(sol.t, dtm, 1)  # noqa: E731
+            bytes_ = 4 * sol.stage_bytes()
         elif op == "copy":
             a_ = torch.randn(nd * 4, dtype=tdt, device="cuda", generator=gen)
             b_ = torch.empty_like(a_)
