@@ -111,56 +111,29 @@ class Clocks:
 # --------------------------------------------------------------------------- #
 
 
-def build_problem(rank, world, n_per_gpu, dtype):
-    import torch
-
-    from fenicsx_fus_gpu_b200 import precompute as pre
+def build_problem(rank, world, n_per_gpu, dtype, halo_kind):
+    """The demo's preamble through fenicsx_fus_gpu_b200.problem (device geometry,
+    block partition, halo).  Returns the solver, an info dict and the halo kind used."""
+    from fenicsx_fus_gpu_b200 import problem
     from fenicsx_fus_gpu_b200 import substrate as S
-    from fenicsx_fus_gpu_b200 import utils
-    from fenicsx_fus_gpu_b200.scatterer import HaloExchange
-    from fenicsx_fus_gpu_b200.solver import LinearSpectral3D, linear_source
 
-    tdt = torch.float64 if dtype == np.float64 else torch.float32
-    tb = S.element_tables(P, "basix", dtype)
     grid = S.block_grid(world)
     ncells = tuple(n_per_gpu * g for g in grid)
     h = DOMAIN_LENGTH / N_PER_GPU  # the demo's cell size; the box grows with the rank grid
     lengths = tuple(h * n for n in ncells)
-    halo = None
-    if world == 1:
-        mesh = S.create_box(ncells, lengths, dtype=dtype)
-        dofmap = S.tensor_dofmap(mesh, P)
-        ndofs = S.num_dofs(ncells, P)
-        nlocal = ndofs
-    else:
-        part = S.partition_box(ncells, P, world, lengths=lengths, dtype=dtype, ranks=[rank], grid=grid)[0]
-        mesh, dofmap = part.mesh, part.dofmap
-        nlocal = part.index_map.size_local
-        ndofs = nlocal + part.index_map.num_ghosts
-        od, gd = utils.compute_scatterer_data(part.index_map)
-        halo = HaloExchange(None, od, gd, nlocal, dtype)
-    nc = mesh.num_cells
-    nd3 = tb.n**3
-    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()  # noqa: E731
-    x_dofs, x_g = d(mesh.x_dofs), d(mesh.x_g)
-    G = torch.empty((nc, nd3, 6), dtype=tdt, device="cuda")
-    detJ = torch.empty((nc, nd3), dtype=tdt, device="cuda")
-    pre.compute_geometry(G, detJ, (x_dofs, x_g), nc, d(tb.dphi), d(tb.wts))
-    bd1, bd2 = S.boundary_facets(mesh, 2), S.boundary_facets(mesh, 3)  # x=0 source, x=L absorbing
-    dJ1 = torch.empty((bd1.shape[0], tb.n**2), dtype=tdt, device="cuda")
-    dJ2 = torch.empty((bd2.shape[0], tb.n**2), dtype=tdt, device="cuda")
-    pre.compute_boundary_facets_scaled_jacobian_determinant(dJ1, (x_dofs, x_g), d(bd1), d(tb.dphi_f), d(tb.wts_f))
-    pre.compute_boundary_facets_scaled_jacobian_determinant(dJ2, (x_dofs, x_g), d(bd2), d(tb.dphi_f), d(tb.wts_f))
-    fd1 = S.facet_dofmap(dofmap, bd1, tb.local_facet_dof)
-    fd2 = S.facet_dofmap(dofmap, bd2, tb.local_facet_dof)
-    full = lambda n, v: torch.full((n,), v, dtype=tdt, device="cuda")  # noqa: E731
-    dofmap_d = d(dofmap)
-    solver = LinearSpectral3D(
-        P, dtype, ndofs, dofmap_d, G, detJ, tb.dphi_1D, full(nc, 1.0 / RHO / C0 / C0), full(nc, -1.0 / RHO),
-        fd1, dJ1, full(bd1.shape[0], 1.0 / RHO), fd2, dJ2, full(bd2.shape[0], -1.0 / RHO / C0),
-        halo=halo, source=lambda t: linear_source(t, F0, P0, C0))
-    info = dict(ncells_local=nc, ndofs_local=ndofs, nlocal=nlocal, global_cells=ncells,
-                global_dofs=S.num_dofs(ncells, P), grid=grid, h=h, detJ=detJ, tb=tb, dofmap=dofmap_d)
+    used = halo_kind if world > 1 else "none"
+    try:
+        su = problem.box_setup(P, ncells, lengths, dtype, rank, world, grid=grid, halo_kind=halo_kind)
+    except Exception as e:  # peer memory unavailable on this box: NCCL send/recv round instead
+        if halo_kind != "p2p" or world == 1:
+            raise
+        print(f"[bench] peer-memory halo unavailable ({e!r}); using the NCCL halo", file=sys.stderr, flush=True)
+        used = "nccl"
+        su = problem.box_setup(P, ncells, lengths, dtype, rank, world, grid=grid, halo_kind="nccl")
+    solver = problem.linear_solver(su, source_facets=[2], absorbing_facets=[3], rho=RHO, c0=C0, f0=F0, p0=P0)
+    info = dict(ncells_local=su.mesh.num_cells, ndofs_local=su.ndofs, nlocal=su.nlocal, global_cells=ncells,
+                global_dofs=su.global_dofs, grid=grid, h=h, detJ=su.dev["detJ"], tb=su.tables,
+                dofmap=su.dev["dofmap"], halo=used)
     return solver, info
 
 
@@ -289,6 +262,8 @@ def main():
     ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU, help="cells per direction per GPU (default: the demo's 80)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU halo: fused put/get kernels over NVLink peer memory, or NCCL send/recv")
     ap.add_argument("--no-graph", action="store_true", help="launch the steps eagerly instead of replaying a CUDA graph")
     ap.add_argument("--watchdog", type=int, default=0, help="dump all Python stacks to stderr after this many seconds")
     ap.add_argument("-v", "--verbose", action="store_true")
@@ -340,7 +315,10 @@ def main():
     dtype = np.float64 if a.dtype == "f64" else np.float32
     s = np.dtype(dtype).itemsize
     log("building the problem")
-    solver, info = build_problem(rank, world, a.n_per_gpu, dtype)
+    solver, info = build_problem(rank, world, a.n_per_gpu, dtype, a.halo)
+    config["parallelism"] = (f"block partition x{world}, halo: " +
+                             {"p2p": "fused put/get kernels over NVLink peer memory", "nccl": "NCCL send/recv",
+                              "none": "none (1 GPU)"}[info["halo"]])
     solver.use_graph = not a.no_graph
     log(f"problem built: {info['ndofs_local']} local dofs, {info['ncells_local']} cells")
     dt = cfl_dt(info["h"])

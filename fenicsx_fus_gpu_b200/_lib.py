@@ -41,6 +41,8 @@ def _sigs():
         "fus_unpack_rev": [P, P, P, L, P],
         "fus_pack_multi": [P, I, P, P, L, L, P],
         "fus_unpack_multi": [P, P, I, P, L, L, I, P],
+        "fus_halo_put": [P, I, P, P, P, P, L, P],
+        "fus_halo_get_add": [P, I, P, P, P, P, L, P],
         "fus_rk_open": [P, P, P, P, P, P, P, P, T, I, L, P],
         "fus_rk_close": [P, P, P, P, P, P, P, P, P, T, T, I, L, P, P],
         "fus_rk_close_westervelt": [P, P, P, P, P, P, P, P, P, P, T, T, I, L, P, P],

@@ -25,7 +25,7 @@ import numpy as np
 from . import precompute as pre
 from . import substrate as S
 from . import utils
-from .scatterer import HaloExchange
+from .scatterer import HaloExchange, P2PHaloExchange, SymmFabric
 from .solver import LinearSpectral3D, WesterveltSpectral3D, linear_source, westervelt_source
 
 
@@ -44,7 +44,7 @@ class Setup:
     nlocal: int  # owned
     global_dofs: int
     global_cells: tuple
-    halo: HaloExchange | None
+    halo: object | None
     dev: dict = field(default_factory=dict)  # device tensors: dofmap, G, detJ, x_dofs, x_g, tables
     h: float = 0.0
 
@@ -56,7 +56,8 @@ def _d(a):
 
 
 def box_setup(P, ncells, lengths, dtype=np.float64, rank=0, world=1, comm=None, grid=None,
-              perturb=0.0, seed=0, order="basix", max_halo_vecs=3, scatter_data=None) -> Setup:
+              perturb=0.0, seed=0, order="basix", max_halo_vecs=3, scatter_data=None,
+              halo_kind="nccl", fabric=None) -> Setup:
     """Mesh part, dofmap, halo and device geometry of rank ``rank`` of ``world``.
 
     ``comm``: torch.distributed group / transport for the halo (None = world
@@ -85,7 +86,13 @@ def box_setup(P, ncells, lengths, dtype=np.float64, rank=0, world=1, comm=None, 
             od, gd = scatter_data
         else:
             od, gd = utils.compute_scatterer_data(part.index_map, comm)
-        halo = HaloExchange(comm, od, gd, nlocal, dtype, max_vecs=max_halo_vecs)
+        if halo_kind == "p2p":
+            # halo fused into two kernels over NVLink peer memory (scatterer.P2PHaloExchange)
+            if fabric is None:
+                fabric = SymmFabric(P2PHaloExchange.arena_bytes(ndofs, dtype), comm)
+            halo = P2PHaloExchange(fabric, od, gd, nlocal, ndofs - nlocal, dtype)
+        else:
+            halo = HaloExchange(comm, od, gd, nlocal, dtype, max_vecs=max_halo_vecs)
     nc = mesh.num_cells
     nd3 = tb.n**3
     dev = dict(dofmap=_d(dofmap), x_dofs=_d(mesh.x_dofs), x_g=_d(mesh.x_g), dphi=_d(tb.dphi), wts=_d(tb.wts),

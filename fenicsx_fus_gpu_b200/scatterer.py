@@ -366,3 +366,206 @@ def scatter_reverse(comm, owners_data, ghosts_data, N, float_type):
 
     scatter.halo = halo
     return scatter
+
+
+# --------------------------------------------------------------------------- #
+# halo exchange over NVLink peer memory (no NCCL in the data path)
+# --------------------------------------------------------------------------- #
+
+
+class SymmFabric:
+    """Peer-addressable device memory for one process per GPU: a symmetric
+    arena (``torch.distributed._symmetric_memory``: CUDA VMM allocations mapped
+    into every peer over NVLink/NVSwitch) plus its signal-pad barrier."""
+
+    def __init__(self, arena_bytes: int, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.size = dist.get_world_size(self.group)
+        t = torch.tensor([int(arena_bytes)], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)  # same size everywhere
+        self.arena_bytes = (int(t.item()) + 255) // 256 * 256
+        self.arena = symm.empty(self.arena_bytes, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+        self.hdl = symm.rendezvous(self.arena, self.group)
+        self.base = [int(p) for p in self.hdl.buffer_ptrs]
+        self._used = 0
+        self._channel = 0
+
+    def alloc(self, numel: int, tdtype, slot_numel: int | None = None):
+        """Carve a tensor out of the arena.  Every rank must make the same
+        sequence of calls; ``slot_numel`` (the maximum over ranks) keeps the
+        offsets identical when the ranks' sizes differ."""
+        import torch
+
+        item = torch.empty(0, dtype=tdtype).element_size()
+        slot = (int(slot_numel if slot_numel is not None else numel) * item + 255) // 256 * 256
+        if self._used + slot > self.arena_bytes:
+            raise RuntimeError("SymmFabric: arena exhausted")
+        out = self.arena[self._used:self._used + numel * item].view(tdtype)
+        self._used += slot
+        out.zero_()
+        return out
+
+    def peer_ptr(self, rank: int, t):
+        return self.base[rank] + (t.data_ptr() - self.base[self.rank])
+
+    def barrier(self):
+        self.hdl.barrier(channel=0)
+
+    def max_over_ranks(self, v: int) -> int:
+        import torch
+        import torch.distributed as dist
+
+        t = torch.tensor([int(v)], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return int(t.item())
+
+    def exchange_index_lists(self, send, dests, recv_sizes, sources):
+        from . import utils
+
+        return utils.exchange_index_lists(send, dests, recv_sizes, sources, self.group)
+
+
+class _LocalFabric:
+    """The same interface with the ranks emulated by threads of one process on
+    one GPU: a peer's memory is just another local buffer."""
+
+    def __init__(self, cluster: LocalCluster, rank: int, arena_bytes: int):
+        import torch
+
+        self.cluster, self.rank, self.size = cluster, rank, cluster.size
+        self.arena_bytes = (self.max_over_ranks(arena_bytes) + 255) // 256 * 256
+        self.arena = torch.zeros(self.arena_bytes, dtype=torch.uint8, device="cuda")
+        with cluster._lock:
+            cluster._mail[("arena", rank)] = self.arena
+        cluster._barrier.wait()
+        self.base = [cluster._mail[("arena", r)].data_ptr() for r in range(self.size)]
+        cluster._barrier.wait()
+        self._used = 0
+
+    alloc = SymmFabric.alloc
+    peer_ptr = SymmFabric.peer_ptr
+
+    def barrier(self):
+        # every rank has ENQUEUED its work on the shared stream: stream order does the rest
+        self.cluster._barrier.wait()
+
+    def max_over_ranks(self, v: int) -> int:
+        cl = self.cluster
+        with cl._lock:
+            cl._mail[("max", self.rank)] = int(v)
+        cl._barrier.wait()
+        out = max(cl._mail[("max", r)] for r in range(self.size))
+        cl._barrier.wait()
+        return out
+
+    def exchange_index_lists(self, send, dests, recv_sizes, sources):
+        cl = self.cluster
+        with cl._lock:
+            for s, d in zip(send, dests):
+                cl._mail[("idx", self.rank, int(d))] = s
+        cl._barrier.wait()
+        out = [cl._mail[("idx", int(s), self.rank)] for s in sources]
+        cl._barrier.wait()
+        return out
+
+
+def local_fabric(cluster: LocalCluster, rank: int, arena_bytes: int):
+    return _LocalFabric(cluster, rank, arena_bytes)
+
+
+class P2PHaloExchange:
+    """Halo exchange fused into two kernels over NVLink peer memory.
+
+    forward  = ``fus_halo_put`` (owned values stored straight into the peers'
+    ghost slots) + one barrier; reverse = barrier + ``fus_halo_get_add`` (ghost
+    partial sums loaded straight from the peers and added) + barrier.  No
+    staging buffers, no NCCL, no pack/unpack launches: 2 + 3 small launches per
+    RK stage instead of 2 x (pack + grouped send/recv + unpack).
+
+    Vectors that take part (``un``, ``vn``, ``b``, ``m``) must be allocated
+    with ``alloc`` so that every peer can address them.  Because peers write
+    into the ghost slots directly, the owner of a vector must not write its own
+    ghost region between exchanges (the fused solvers update owned entries only
+    when this exchange is used).
+    """
+
+    p2p = True
+
+    def __init__(self, fabric, owners_data, ghosts_data, N, nghost, float_type):
+        import torch
+
+        self.fabric = fabric
+        self.N, self.nghost = int(N), int(nghost)
+        self.dtype = np.dtype(float_type)
+        self.tdtype = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32}[self.dtype]
+        o_idx, o_size, o_ranks = owners_data
+        g_idx, g_size, g_ranks = ghosts_data
+        self.ghost_ranks = [int(r) for r in np.asarray(g_ranks).ravel()]
+        ghost_sizes = [int(s) for s in np.asarray(g_size).ravel()]
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.idx = _cat_index(g_idx).to(dev)
+        self.n = int(self.idx.numel())
+        # where each of my shared dofs sits in the neighbour's vector: the neighbour's
+        # owners_idx list for me (same order as my ghosts_idx, cuda/utils.py:57-73) + its N
+        send = [np.ascontiguousarray(np.asarray(ix, dtype=np.int64) + self.N) for ix in o_idx]
+        recv = fabric.exchange_index_lists(send, [int(r) for r in np.asarray(o_ranks).ravel()],
+                                           ghost_sizes, self.ghost_ranks)
+        self.remote_pos = _cat_index([np.asarray(r, dtype=np.int64) for r in recv]).to(dev)
+        seg = np.repeat(np.arange(len(ghost_sizes), dtype=np.int32), ghost_sizes)
+        self.entry_seg = torch.from_numpy(seg).to(dev)
+        self.slot = fabric.max_over_ranks(self.N + self.nghost)
+        self._tables = {}
+        self._ptrs = (C.c_void_p * 4)()
+
+    @staticmethod
+    def arena_bytes(ndofs_local: int, float_type, nvec: int = 6) -> int:
+        """Arena size for ``nvec`` exchanged vectors of ``ndofs_local`` entries."""
+        return nvec * ((int(ndofs_local) * np.dtype(float_type).itemsize + 255) // 256 * 256 + 256)
+
+    def alloc(self):
+        """A zeroed ``(N + nghost,)`` vector in peer-addressable memory."""
+        return self.fabric.alloc(self.N + self.nghost, self.tdtype, self.slot)
+
+    def _peer_table(self, vecs):
+        import torch
+
+        key = tuple(v.data_ptr() for v in vecs)
+        tab = self._tables.get(key)
+        if tab is None:
+            rows = [[self.fabric.peer_ptr(q, v) for v in vecs] for q in self.ghost_ranks]
+            # int64 view of the (unsigned) device addresses
+            tab = torch.tensor(np.array(rows, dtype=np.uint64).astype(np.int64).reshape(-1)
+                               if rows else np.zeros(0, np.int64), device=self.idx.device)
+            self._tables[key] = tab
+        return tab
+
+    def _launch(self, name, vecs):
+        if not 1 <= len(vecs) <= 4:
+            raise ValueError("P2PHaloExchange: 1..4 vectors per round")
+        if self.n:
+            tab = self._peer_table(vecs)
+            for i, v in enumerate(vecs):
+                self._ptrs[i] = dev(v, self.dtype).ptr
+            check(fn(name, self.dtype)(self._ptrs, len(vecs), tab.data_ptr(), self.idx.data_ptr(),
+                                       self.remote_pos.data_ptr(), self.entry_seg.data_ptr(), self.n,
+                                       current_stream()), name)
+
+    def barrier(self):
+        self.fabric.barrier()
+
+    def forward(self, *vecs):
+        """Owner values -> every ghost copy (cuda/scatterer.py:191-277)."""
+        self._launch("fus_halo_put", vecs)
+        self.fabric.barrier()
+
+    def reverse(self, *vecs):
+        """Ghost partial sums added into the owners (cuda/scatterer.py:104-188).
+        The ghost region keeps its values, as in the reference."""
+        self.fabric.barrier()  # every rank's ghost sums are complete
+        self._launch("fus_halo_get_add", vecs)
+        self.fabric.barrier()  # every rank has read them: they may be overwritten now

@@ -114,11 +114,19 @@ class _RK4:
         self._dphi_host = np.ascontiguousarray(
             dphi_1D.cpu().numpy() if isinstance(dphi_1D, torch.Tensor) else dphi_1D, dtype=self.dtype)
         z = lambda: torch.zeros(self.ndofs, dtype=self.T, device="cuda")  # noqa: E731
+        # With the peer-memory halo (scatterer.P2PHaloExchange) the exchanged vectors live in
+        # peer-addressable memory and only their owned part is updated locally: the ghost
+        # slots are written by the neighbours.
+        self.p2p = bool(getattr(halo, "p2p", False))
+        self.nupd = int(halo.N) if self.p2p else self.ndofs  # entries the vector kernels update
+        zx = halo.alloc if self.p2p else z
         # the reference's 14 vectors (cuda/demo_linear_box.py:380-385, 464-471)
         # shrink to 9: u v u0 v0 ku kv un b m  (vn lives in ku; g, u_n, v_n fused away)
         self.u, self.v, self.u0, self.v0 = z(), z(), z(), z()
-        self.ku, self.kv, self.un, self.b = z(), z(), z(), z()
-        self.m = z()
+        self.kv = z()
+        self.ku, self.un, self.b = zx(), zx(), zx()
+        self.m = zx()
+        self._zx = zx
         self.step_dev = torch.zeros(1, dtype=torch.int64, device="cuda")
         self.gtab = None
         self.t = 0.0
@@ -183,8 +191,21 @@ class _RK4:
         check(fn("fus_rk_open", self.dtype)(
             self.u.data_ptr(), self.v.data_ptr(), self.u0.data_ptr(), self.v0.data_ptr(),
             self.ku.data_ptr(), self.kv.data_ptr(), self.un.data_ptr(), self.b.data_ptr(), 0.0, 1,
-            self.ndofs, current_stream()), "fus_rk_open")
+            self.nupd, current_stream()), "fus_rk_open")
+        if self.p2p:
+            self._zero_ghosts()
+            self.halo.barrier()  # nobody's first put may land before this rank's open has run
         self._opened = True
+
+    def _zero_ghosts(self):
+        """Peer-memory halo: the close kernel covers the owned entries only, so the
+        ghost part of the accumulators (b, and m for Westervelt) is cleared here."""
+        ng = self.ndofs - self.nupd
+        if ng > 0:
+            off = self.nupd * self.dtype.itemsize
+            check(fn("fus_fill", self.dtype)(0.0, self.b.data_ptr() + off, ng, current_stream()), "fus_fill")
+            if self.westervelt:
+                check(fn("fus_fill", self.dtype)(0.0, self.m.data_ptr() + off, ng, current_stream()), "fus_fill")
 
     def _assemble(self, stage, g, dg, use_table):  # pragma: no cover - abstract
         raise NotImplementedError
@@ -212,6 +233,8 @@ class _RK4:
             self._assemble(i, g, dg, use_table)
             self._halo_reverse()
             self._close(i, dt, use_table)
+            if self.p2p:
+                self._zero_ghosts()
 
     # ---- public --------------------------------------------------------------
     def init(self):
@@ -298,6 +321,8 @@ class _RK4:
         for t, s in zip(self._state(), saved):
             t.copy_(s)
         self.step_dev.copy_(step0)
+        if self.p2p:
+            self.halo.barrier()  # every rank has restored its ghost slots before anyone's next put
         self._graph_dt, self._graph_tab = dt, self.gtab.data_ptr()
         try:
             g = torch.cuda.CUDAGraph()
@@ -370,7 +395,7 @@ class LinearSpectral3D(_RK4):
             self.u.data_ptr(), self.v.data_ptr(), self.u0.data_ptr(), self.v0.data_ptr(),
             self.ku.data_ptr(), None, self.un.data_ptr(), self.b.data_ptr(), self.m.data_ptr(),
             B_RUNGE[stage] * dt, 0.0 if last else A_RUNGE[stage + 1] * dt, 2 if last else 1,
-            self.ndofs, self.step_dev.data_ptr() if count_step else None, current_stream()),
+            self.nupd, self.step_dev.data_ptr() if count_step else None, current_stream()),
             "fus_rk_close")
 
 
@@ -405,7 +430,7 @@ class WesterveltSpectral3D(_RK4):
         bd2 = _dev(bfacet_dofmap2, torch.int32) if bfacet_dofmap2 is not None else e(torch.int32)
         # steady LHS m0 (cuda/demo_nonlinear_bowl.py:459-469)
         ones = torch.ones(self.ndofs, dtype=self.T, device="cuda")
-        self.m0 = torch.zeros(self.ndofs, dtype=self.T, device="cuda")
+        self.m0 = self._zx()  # reverse-exchanged once below: peer-addressable with the P2P halo
         self._mass(ones, c1, self.m0, self.detJ, self.dofmap)
         if bd2.shape[0]:
             self._mass(ones, _dev(facet_coeff1_2, self.T), self.m0, _dev(detJ_f2, self.T), bd2)
@@ -441,7 +466,7 @@ class WesterveltSpectral3D(_RK4):
             self.u.data_ptr(), self.v.data_ptr(), self.u0.data_ptr(), self.v0.data_ptr(),
             self.ku.data_ptr(), None, self.un.data_ptr(), self.b.data_ptr(), self.m.data_ptr(),
             self.m0.data_ptr(), B_RUNGE[stage] * dt, 0.0 if last else A_RUNGE[stage + 1] * dt,
-            2 if last else 1, self.ndofs, self.step_dev.data_ptr() if count_step else None,
+            2 if last else 1, self.nupd, self.step_dev.data_ptr() if count_step else None,
             current_stream()), "fus_rk_close_westervelt")
 
     def stage_bytes(self):

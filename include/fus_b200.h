@@ -150,6 +150,28 @@ int fus_unpack_multi_f64(const double* in, double* const* out, int nvec, const i
 int fus_unpack_multi_f32(const float* in, float* const* out, int nvec, const int64_t* index,
                          int64_t n, int64_t offset, int add, void* stream);
 
+/* Halo exchange through NVLink peer memory - the whole of
+ * cuda/scatterer.py:191-277 (forward) / :104-188 (reverse) as ONE kernel each:
+ *   put     : peer_v[remote_pos[e]]  = local_v[idx[e]]     (owner -> ghost copies)
+ *   get_add : local_v[idx[e]]       += peer_v[remote_pos[e]] (ghost sums -> owner)
+ * e runs over the concatenated ghosts_data lists (MY owned dofs that are ghosts on
+ * a neighbour); entry_seg[e] is the neighbour segment, peer[seg*nvec + v] the device
+ * address of vector v in that neighbour's memory (a peer mapping), remote_pos[e]
+ * the entry's position in the neighbour's vector.  `local` and `peer` are arrays
+ * of nvec (<= 4) pointers: `local` in HOST memory (read at launch), `peer` in
+ * DEVICE memory.  Ordering across GPUs (a barrier after put, before and after
+ * get_add) is the caller's. */
+int fus_halo_put_f64(double* const* local, int nvec, const uint64_t* peer, const int64_t* idx,
+                     const int64_t* remote_pos, const int32_t* entry_seg, int64_t n, void* stream);
+int fus_halo_put_f32(float* const* local, int nvec, const uint64_t* peer, const int64_t* idx,
+                     const int64_t* remote_pos, const int32_t* entry_seg, int64_t n, void* stream);
+int fus_halo_get_add_f64(double* const* local, int nvec, const uint64_t* peer, const int64_t* idx,
+                         const int64_t* remote_pos, const int32_t* entry_seg, int64_t n,
+                         void* stream);
+int fus_halo_get_add_f32(float* const* local, int nvec, const uint64_t* peer, const int64_t* idx,
+                         const int64_t* remote_pos, const int32_t* entry_seg, int64_t n,
+                         void* stream);
+
 /* --------------------------------------------------------------------- *
  * Fused RK4 stage kernels.  Replace the 13 vector launches per stage of
  * cuda/demo_linear_box.py:491-563 (numba-cpu/demo_linear_box.py:425-459,

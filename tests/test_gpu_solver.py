@@ -184,14 +184,15 @@ def test_halo_exchange_vs_reference_fixture(golden_dir, name):
         assert np.array_equal(b2[N:], 2.0 * f[N:])
 
 
+@pytest.mark.parametrize("kind", ["nccl-shaped", "p2p"])
 @pytest.mark.parametrize("R,N,P", [(2, (4, 3, 3), 3), (8, (4, 4, 4), 2), (4, (4, 4, 2), 4)])
-def test_linear_rk4_partitioned_vs_serial_oracle(R, N, P):
+def test_linear_rk4_partitioned_vs_serial_oracle(R, N, P, kind):
     """The multi-GPU algorithm end to end on one GPU: R partitions, each with
     its own solver + halo exchange, against the single-rank oracle run."""
     import problems
     from fenicsx_fus_gpu_b200 import substrate as S
     from fenicsx_fus_gpu_b200 import utils
-    from fenicsx_fus_gpu_b200.scatterer import HaloExchange, LocalCluster
+    from fenicsx_fus_gpu_b200.scatterer import HaloExchange, LocalCluster, P2PHaloExchange, local_fabric
 
     dtt = np.float64
     L = (0.012, 0.01, 0.011)
@@ -208,7 +209,13 @@ def test_linear_rk4_partitioned_vs_serial_oracle(R, N, P):
         p = parts[r]
         nd = p.index_map.size_local + p.index_map.num_ghosts
         d = problems.linear_problem(P, None, None, dtt, mesh=p.mesh, dofmap=p.dofmap, ndofs=nd)
-        halo = HaloExchange(transport, sdata[r][0], sdata[r][1], p.index_map.size_local, dtt)
+        if kind == "p2p":  # halo fused into put / get_add kernels over peer-addressable memory
+            ndmax = max(q.index_map.size_local + q.index_map.num_ghosts for q in parts)
+            fab = local_fabric(transport.cluster, r, P2PHaloExchange.arena_bytes(ndmax, dtt))
+            halo = P2PHaloExchange(fab, sdata[r][0], sdata[r][1], p.index_map.size_local,
+                                   p.index_map.num_ghosts, dtt)
+        else:  # pack -> grouped send/recv -> unpack
+            halo = HaloExchange(transport, sdata[r][0], sdata[r][1], p.index_map.size_local, dtt)
         s = _linear_solver(d, dtt, halo=halo, use_graph=False)
         s.init()
         s.rk4(0.0, dt, nsteps)
@@ -305,3 +312,58 @@ def test_full_size_properties_demo_linear_box():
     s.init()
     s.rk4(0.0, 1e-8, 2)
     assert float(s.u.abs().max()) == 0.0 and float(s.v.abs().max()) == 0.0
+
+
+def test_westervelt_rk4_partitioned_p2p_vs_serial_oracle():
+    """Westervelt stage over 4 emulated ranks with the peer-memory halo (forward of
+    (un, vn), reverse of (b, m) in one get_add) against the single-rank oracle."""
+    import problems
+    from fenicsx_fus_gpu_b200 import substrate as S
+    from fenicsx_fus_gpu_b200 import utils
+    from fenicsx_fus_gpu_b200.scatterer import LocalCluster, P2PHaloExchange, local_fabric
+    from fenicsx_fus_gpu_b200.solver import WesterveltSpectral3D, westervelt_source
+    from oracle import oracle as orc
+
+    dtt, P, N, L, R, nsteps = np.float64, 3, (4, 4, 3), (0.006, 0.006, 0.0045), 4, 6
+    d = problems.westervelt_problem(P, N, L, dtt, perturb=0.1, seed=9)
+    dt = problems.cfl_dt(P, 0.0015, d.c0, d.f0, cfl=0.4)
+    ones = np.ones(d.ndofs)
+    m0 = np.zeros(d.ndofs)
+    orc.mass_operator(ones, d.cell_coeff1, m0, d.detJ, d.dofmap)
+    orc.mass_operator(ones, d.facet_coeff1_2, m0, d.detJ_f2, d.bfacet_dofmap2)
+    prob = orc.WesterveltProblem(d.P, d.dofmap, d.G, d.detJ, d.tb.dphi_1D, d.cell_coeff2, d.cell_coeff3,
+                                 d.cell_coeff4, d.cell_coeff5, m0, d.bfacet_dofmap1, d.detJ_f1,
+                                 d.facet_coeff1_1, d.facet_coeff2_1, d.bfacet_dofmap2, d.detJ_f2,
+                                 d.facet_coeff2_2, d.f0, d.p0, d.c0)
+    u_ref, v_ref = np.zeros(d.ndofs), np.zeros(d.ndofs)
+    orc.westervelt_rk4(prob, u_ref, v_ref, 0.0, dt, nsteps)
+
+    parts = S.partition_box(N, P, R, lengths=L, dtype=dtt, perturb=0.1, seed=9)
+    sdata = utils.compute_scatterer_data_all([p.index_map for p in parts])
+    ndmax = max(q.index_map.size_local + q.index_map.num_ghosts for q in parts)
+
+    def body(r, transport):
+        p = parts[r]
+        nd = p.index_map.size_local + p.index_map.num_ghosts
+        w = problems.westervelt_problem(P, None, None, dtt, mesh=p.mesh, dofmap=p.dofmap, ndofs=nd)
+        fab = local_fabric(transport.cluster, r, P2PHaloExchange.arena_bytes(ndmax, dtt))
+        halo = P2PHaloExchange(fab, sdata[r][0], sdata[r][1], p.index_map.size_local, p.index_map.num_ghosts, dtt)
+        s = WesterveltSpectral3D(
+            P, dtt, nd, w.dofmap, w.G, w.detJ, w.tb.dphi_1D, w.cell_coeff1, w.cell_coeff2, w.cell_coeff3,
+            w.cell_coeff4, w.cell_coeff5, w.bfacet_dofmap1, w.detJ_f1, w.facet_coeff1_1, w.facet_coeff2_1,
+            w.bfacet_dofmap2, w.detJ_f2, w.facet_coeff1_2, w.facet_coeff2_2, halo=halo,
+            source=lambda t: westervelt_source(t, w.f0, w.p0, w.c0), use_graph=False)
+        s.init()
+        s.rk4(0.0, dt, nsteps)
+        torch.cuda.synchronize()
+        return s.u.cpu().numpy(), s.v.cpu().numpy()
+
+    out = LocalCluster(R).run(body)
+    u, v = np.zeros_like(u_ref), np.zeros_like(v_ref)
+    for r, p in enumerate(parts):
+        nl = p.index_map.size_local
+        u[p.local_to_serial[:nl]] = out[r][0][:nl]
+        v[p.local_to_serial[:nl]] = out[r][1][:nl]
+    assert np.linalg.norm(u_ref) > 0
+    assert rel_l2(u, u_ref) < 1e-12
+    assert rel_l2(v, v_ref) < 1e-12
