@@ -311,19 +311,22 @@ def _structured_connectivity(ncells, P, pos=None, origin=(0, 0, 0), grid=None):
     if grid is None:
         grid = (P * Nx + 1, P * Ny + 1, P * Nz + 1)
     GY, GZ = grid[1], grid[2]
-    cx, cy, cz = np.meshgrid(np.arange(Nx), np.arange(Ny), np.arange(Nz), indexing="ij")
-    cx, cy, cz = cx.ravel(), cy.ravel(), cz.ravel()
     if pos is None:  # P1 geometry: vertex order, x fastest
         v = np.arange(8)
         ox, oy, oz = v & 1, (v >> 1) & 1, (v >> 2) & 1
     else:
         I, J, K = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
         ox, oy, oz = pos[I].ravel(), pos[J].ravel(), pos[K].ravel()
-    gx = origin[0] + cx[:, None] * P + ox[None, :]
-    gy = origin[1] + cy[:, None] * P + oy[None, :]
-    gz = origin[2] + cz[:, None] * P + oz[None, :]
-    out = (gx * GY + gy) * GZ + gz
-    return out.astype(np.int32) if out.max(initial=0) < 2**31 else out
+    # index = base(cell) + offset(local node): both separable, one broadcast add
+    gx0 = (origin[0] + np.arange(Nx, dtype=np.int64) * P) * (GY * GZ)
+    gy0 = (origin[1] + np.arange(Ny, dtype=np.int64) * P) * GZ
+    gz0 = origin[2] + np.arange(Nz, dtype=np.int64) * P
+    base = (gx0[:, None, None] + gy0[None, :, None] + gz0[None, None, :]).ravel()
+    off = (ox.astype(np.int64) * GY + oy) * GZ + oz
+    top = (int(base.max(initial=0)) + int(off.max(initial=0))) if base.size else 0
+    if top < 2**31:
+        return base.astype(np.int32)[:, None] + off.astype(np.int32)[None, :]
+    return base[:, None] + off[None, :]
 
 
 def tensor_dofmap(mesh: BoxMesh, P: int, order: str = "basix") -> np.ndarray:
@@ -535,24 +538,27 @@ def partition_box(
         mesh = BoxMesh(tuple(int(v) for v in nc), x_dofs, x_g, tuple(int(v) for v in c0),
                        ncells, tuple(float(v) for v in lengths))
 
-        # --- dofs touched by this part: the node box [P*c0, P*(c0+nc)]
+        # --- dofs touched by this part: the node box [P*c0, P*(c0+nc)].  Every
+        # per-node quantity is separable over the axes, so it is built from three
+        # 1-D arrays and broadcast once (the node box has 1.3e8 entries at 125^3 cells).
         lo = [P * c0[d] for d in range(3)]
         ext = [P * nc[d] + 1 for d in range(3)]
-        NX, NY, NZ = np.meshgrid(
-            np.arange(lo[0], lo[0] + ext[0]),
-            np.arange(lo[1], lo[1] + ext[1]),
-            np.arange(lo[2], lo[2] + ext[2]),
-            indexing="ij",
-        )
-        NX, NY, NZ = NX.ravel(), NY.ravel(), NZ.ravel()
-        gnew, own = new_global(NX, NY, NZ)
+        g1 = [np.arange(lo[d], lo[d] + ext[d], dtype=np.int64) for d in range(3)]
+        b1 = [owner_block_1d(d, g1[d]) for d in range(3)]
+        lo1 = [P * starts[d][b1[d]] + (b1[d] > 0) for d in range(3)]
+        n1 = [P * starts[d][b1[d] + 1] + 1 - lo1[d] for d in range(3)]
+        bc = lambda v, d: v.reshape([-1 if e == d else 1 for e in range(3)])  # noqa: E731
+        own = ((bc(b1[0], 0) * R[1] + bc(b1[1], 1)) * R[2] + bc(b1[2], 2)).astype(np.int32).ravel()
+        gnew = (((bc(g1[0] - lo1[0], 0) * bc(n1[1], 1) + bc(g1[1] - lo1[1], 1)) * bc(n1[2], 2)
+                 + bc(g1[2] - lo1[2], 2)).ravel())
+        gnew += offsets[own]
         is_owned = own == rank
         nlocal = int(is_owned.sum())
         assert nlocal == owned[rank]
+        nnode = gnew.size
         # local numbering: owned -> gnew - offset (lexicographic in the owned
         # box), ghosts -> appended in ascending global order
-        local = np.empty(NX.size, dtype=np.int64)
-        local[is_owned] = gnew[is_owned] - offsets[rank]
+        local = gnew - offsets[rank]
         gh_pos = np.where(~is_owned)[0]
         gh_sort = gh_pos[np.argsort(gnew[gh_pos], kind="stable")]
         local[gh_sort] = nlocal + np.arange(gh_sort.size)
@@ -561,41 +567,35 @@ def partition_box(
 
         # local dofmap through the part's node box
         boxmap = _structured_connectivity(nc, P, pos)  # indices into the node box
-        dofmap = np.ascontiguousarray(local[boxmap], dtype=np.int32)
+        local32 = local.astype(np.int32) if nnode < 2**31 else local
+        dofmap = np.ascontiguousarray(local32[boxmap], dtype=np.int32)
+        del boxmap, local32
 
-        l2g = np.empty(NX.size, dtype=np.int64)
+        l2g = np.empty(nnode, dtype=np.int64)
         l2g[local] = gnew
-        l2s = np.empty(NX.size, dtype=np.int64)
-        l2s[local] = (NX * G[1] + NY) * G[2] + NZ
+        l2s = np.empty(nnode, dtype=np.int64)
+        l2s[local] = ((bc(g1[0], 0) * G[1] + bc(g1[1], 1)) * G[2] + bc(g1[2], 2)).ravel()
 
         # --- index_to_dest_ranks: for each owned dof, ranks that ghost it.
-        # A rank-block touches node g along axis d if P*s_b <= g <= P*s_{b+1}.
-        ox, oy, oz = NX[is_owned], NY[is_owned], NZ[is_owned]
-        oloc = local[is_owned]
-
-        def touching(d, g):
-            # blocks touching node g along axis d: the owner block and, when g
-            # is on an interface (g == P*starts[b+1], b+1 < R), block b+1
-            b = owner_block_1d(d, g)
-            on_if = (g == P * starts[d][b + 1]) & (b + 1 < R[d])
-            return b, on_if
-
-        bxo, ifx = touching(0, ox)
-        byo, ify = touching(1, oy)
-        bzo, ifz = touching(2, oz)
-        # (owned dof, destination rank) pairs: the owner block plus one step
-        # along every axis on which the dof lies on an interface
+        # A rank-block touches node g along axis d if P*s_b <= g <= P*s_{b+1}:
+        # the owner block and, when g is on an interface (g == P*starts[b+1],
+        # b+1 < R), block b+1.  Owned nodes form a sub-box of the node box, so the
+        # (owned dof, destination rank) pairs are Cartesian products of per-axis sets.
+        mine = (bx, by, bz)
+        own1 = [np.nonzero(b1[d] == mine[d])[0] for d in range(3)]  # owned positions per axis
+        if1 = [g1[d][own1[d]] == P * starts[d][mine[d] + 1] if mine[d] + 1 < R[d]
+               else np.zeros(own1[d].size, bool) for d in range(3)]
         pair_dof, pair_rank = [], []
         for dx in (0, 1):
             for dy in (0, 1):
                 for dz in (0, 1):
                     if dx == dy == dz == 0:
                         continue
-                    msk = (ifx if dx else True) & (ify if dy else True) & (ifz if dz else True)
-                    sel = np.nonzero(np.broadcast_to(msk, ox.shape))[0]
-                    if sel.size:
-                        pair_dof.append(oloc[sel])
-                        pair_rank.append(rank_of(bxo[sel] + dx, byo[sel] + dy, bzo[sel] + dz))
+                    sel = [own1[d][if1[d]] if dd else own1[d] for d, dd in enumerate((dx, dy, dz))]
+                    if all(v.size for v in sel):
+                        flat = ((bc(sel[0], 0) * ext[1] + bc(sel[1], 1)) * ext[2] + bc(sel[2], 2)).ravel()
+                        pair_dof.append(local[flat])
+                        pair_rank.append(np.full(flat.size, rank_of(bx + dx, by + dy, bz + dz), np.int64))
         if pair_dof:
             pd = np.concatenate(pair_dof)
             pr = np.concatenate(pair_rank)
