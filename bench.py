@@ -111,29 +111,58 @@ class Clocks:
 # --------------------------------------------------------------------------- #
 
 
-def build_problem(rank, world, n_per_gpu, dtype, halo_kind):
+WORKLOADS = {
+    # name: degree, c0, rho, f0, reference cell size h, CFL, BASELINE.json config it stands for
+    "linear_box": dict(P=4, c0=1500.0, rho=1000.0, f0=0.5e6, h=0.12 / 80, cfl=0.65, n=80, nonlinear=False,
+                       label="demo_linear_box: linear wave, RK4 (BASELINE.json configs[1])"),
+    # cuda/demo_linear_piston.py:53-66: degree 5, piston of radius 10 mm on z=0, every other exterior facet absorbing
+    "linear_piston": dict(P=5, c0=1500.0, rho=1000.0, f0=0.5e6, h=0.12 / 93, cfl=0.65, n=58, nonlinear=False,
+                          label="demo_linear_piston: planar piston + absorbing facets, RK4 (BASELINE.json configs[2])"),
+    # cuda/demo_nonlinear_bowl.py:61-75,122: Westervelt, c=1480, f=1.1 MHz, beta=3.5, alpha=0.2 dB, CFL 0.4
+    "nonlinear_bowl": dict(P=4, c0=1480.0, rho=1000.0, f0=1.1e6, h=0.08 / 198, cfl=0.4, n=99, nonlinear=True,
+                           label="demo_nonlinear_bowl: Westervelt, source disc + all facets absorbing, RK4 "
+                                 "(BASELINE.json configs[3])"),
+}
+
+
+def build_problem(rank, world, n_per_gpu, dtype, halo_kind, workload="linear_box", degree=None):
     """The demo's preamble through fenicsx_fus_gpu_b200.problem (device geometry,
-    block partition, halo).  Returns the solver, an info dict and the halo kind used."""
+    block partition, halo).  Returns the solver and an info dict."""
     from fenicsx_fus_gpu_b200 import problem
     from fenicsx_fus_gpu_b200 import substrate as S
 
+    W = WORKLOADS[workload]
+    deg = degree or W["P"]
     grid = S.block_grid(world)
     ncells = tuple(n_per_gpu * g for g in grid)
-    h = DOMAIN_LENGTH / N_PER_GPU  # the demo's cell size; the box grows with the rank grid
+    h = W["h"]  # the demo's cell size; the box grows with the rank grid
     lengths = tuple(h * n for n in ncells)
     used = halo_kind if world > 1 else "none"
     try:
-        su = problem.box_setup(P, ncells, lengths, dtype, rank, world, grid=grid, halo_kind=halo_kind)
+        su = problem.box_setup(deg, ncells, lengths, dtype, rank, world, grid=grid, halo_kind=halo_kind)
     except Exception as e:  # peer memory unavailable on this box: NCCL send/recv round instead
         if halo_kind != "p2p" or world == 1:
             raise
         print(f"[bench] peer-memory halo unavailable ({e!r}); using the NCCL halo", file=sys.stderr, flush=True)
         used = "nccl"
-        su = problem.box_setup(P, ncells, lengths, dtype, rank, world, grid=grid, halo_kind="nccl")
-    solver = problem.linear_solver(su, source_facets=[2], absorbing_facets=[3], rho=RHO, c0=C0, f0=F0, p0=P0)
+        su = problem.box_setup(deg, ncells, lengths, dtype, rank, world, grid=grid, halo_kind="nccl")
+    if workload == "linear_box":
+        solver = problem.linear_solver(su, source_facets=[2], absorbing_facets=[3], rho=W["rho"], c0=W["c0"],
+                                       f0=W["f0"], p0=P0)
+    elif workload == "linear_piston":
+        piston = problem.disc(0, 1, (0.5 * lengths[0], 0.5 * lengths[1]), 0.01)
+        solver = problem.linear_solver(
+            su, source_facets=[0], absorbing_facets=[0, 1, 2, 3, 4, 5], rho=W["rho"], c0=W["c0"], f0=W["f0"], p0=P0,
+            source_predicate=piston, absorbing_predicate=lambda cen: ~(piston(cen) & (cen[:, 2] < 0.5 * h)))
+    else:
+        centre = (0.5 * lengths[1], 0.5 * lengths[2])
+        solver = problem.westervelt_solver(
+            su, source_facets=[2], absorbing_facets=[0, 1, 2, 3, 4, 5], rho=W["rho"], c0=W["c0"], f0=W["f0"],
+            beta=3.5, alpha_dB=0.2, source_predicate=problem.disc(1, 2, centre, 0.3 * lengths[1]))
     info = dict(ncells_local=su.mesh.num_cells, ndofs_local=su.ndofs, nlocal=su.nlocal, global_cells=ncells,
                 global_dofs=su.global_dofs, grid=grid, h=h, detJ=su.dev["detJ"], tb=su.tables,
-                dofmap=su.dev["dofmap"], halo=used)
+                dofmap=su.dev["dofmap"], halo=used, degree=deg,
+                dt=problem.cfl_time_step(deg, h, W["c0"], W["f0"], W["cfl"]))
     return solver, info
 
 
@@ -259,8 +288,11 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n-per-gpu", type=int, default=N_PER_GPU, help="cells per direction per GPU (default: the demo's 80)")
+    ap.add_argument("--n-per-gpu", type=int, default=0, help="cells per direction per GPU (default: the workload's)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--workload", default="linear_box", choices=sorted(WORKLOADS),
+                    help="which reference demo to time (default: the headline demo_linear_box)")
+    ap.add_argument("--degree", type=int, default=0, help="override the workload's polynomial degree (2..7)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU halo: fused put/get kernels over NVLink peer memory, or NCCL send/recv")
@@ -282,10 +314,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     warmup = max(3, a.warmup)
-    config = {"workload": f"demo_linear_box: linear wave, RK4, degree {P} hexahedra, {a.n_per_gpu}^3 cells per GPU "
-                          f"(BASELINE.json configs[1]), {a.dtype}",
-              "degree": P, "cells_per_gpu": a.n_per_gpu**3, "parallelism": f"block partition x{world}, NCCL halo",
-              "l2": "working set per GPU ~6 GB >> 126 MB L2 (no flush needed)"}
+    W = WORKLOADS[a.workload]
+    deg = a.degree or W["P"]
+    n_per_gpu = a.n_per_gpu or W["n"]
+    config = {"workload": f"{W['label']}, degree {deg} hexahedra, {n_per_gpu}^3 cells per GPU, {a.dtype}",
+              "degree": deg, "cells_per_gpu": n_per_gpu**3, "parallelism": f"block partition x{world}",
+              "l2": "working set per GPU (G + dofmap + 9 vectors, GBs) >> 126 MB L2: no flush needed"}
 
     if a.impl == "reference":
         if rank != 0:
@@ -315,13 +349,13 @@ def main():
     dtype = np.float64 if a.dtype == "f64" else np.float32
     s = np.dtype(dtype).itemsize
     log("building the problem")
-    solver, info = build_problem(rank, world, a.n_per_gpu, dtype, a.halo)
+    solver, info = build_problem(rank, world, n_per_gpu, dtype, a.halo, a.workload, deg)
     config["parallelism"] = (f"block partition x{world}, halo: " +
                              {"p2p": "fused put/get kernels over NVLink peer memory", "nccl": "NCCL send/recv",
                               "none": "none (1 GPU)"}[info["halo"]])
     solver.use_graph = not a.no_graph
     log(f"problem built: {info['ndofs_local']} local dofs, {info['ncells_local']} cells")
-    dt = cfl_dt(info["h"])
+    dt = info["dt"]
     lib = _lib.lib()
 
     def barrier():
@@ -344,7 +378,8 @@ def main():
     log(f"warm-up done (graph={'yes' if solver._graph is not None else 'no: ' + str(solver.graph_error)})")
     lib.fus_reset_launch_count()
     barrier()
-    clocks = Clocks(local_rank)
+    cvd = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip().isdigit()]
+    clocks = Clocks(int(cvd[local_rank]) if local_rank < len(cvd) else local_rank)  # nvidia-smi index of this rank's GPU
     clocks.start()
     time.sleep(0.3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -409,40 +444,70 @@ def main():
     d2h = nsample * s
 
     log("e2e done")
-    # ---- the dominant kernel alone: stiffness launches under CUDA events (roofline) ----
+    # ---- the dominant kernel alone, under CUDA events on the launching stream (roofline):
+    #      3 warm-ups, then `reps` back-to-back launches between one event pair (mean) and
+    #      `reps` individually bracketed launches (min), SURVEY.md 8(d) protocol ----
     nc, nd = info["ncells_local"], info["ndofs_local"]
-    n = P + 1
+    n = deg + 1
     nd3 = n**3
-    K = ops.stiffness_operator(P, dtype)
     gen = torch.Generator(device="cuda").manual_seed(1)
     x = torch.randn(nd, dtype=solver.T, device="cuda", generator=gen)
     y = torch.zeros(nd, dtype=solver.T, device="cuda")
     D = torch.from_numpy(info["tb"].dphi_1D).cuda()
+    tname = "double" if a.dtype == "f64" else "float"
+    if W["nonlinear"]:
+        # the Westervelt stage kernel: both stiffness terms + the cell-mass pair, one pass over G
+        x2 = torch.randn(nd, dtype=solver.T, device="cuda", generator=gen)
+        y2 = torch.zeros(nd, dtype=solver.T, device="cuda")
+        fw = _lib.fn("fus_stiffness_westervelt", dtype)
+        st = torch.cuda.current_stream().cuda_stream
+
+        def launch():
+            rc = fw(x.data_ptr(), solver.c3.data_ptr(), x2.data_ptr(), solver.c4.data_ptr(), solver.c2.data_ptr(),
+                    solver.c5.data_ptr(), y2.data_ptr(), y.data_ptr(), solver.G.data_ptr(), solver.detJ.data_ptr(),
+                    solver.dofmap.data_ptr(), D.data_ptr(), nc, deg, 0, st)
+            assert rc == 0
+        kname = f"stiffness_kernel<{tname},{n},2,1> (fus_stiffness_westervelt_{a.dtype})"
+        # per cell: dofmap + G + detJ + 4 coefficients; per dof: read un, vn, write b, m
+        bytes_stiff = nc * (nd3 * 4 + 6 * nd3 * s + nd3 * s + 4 * s) + 4 * s * nd
+    else:
+        K = ops.stiffness_operator(deg, dtype)
+
+        def launch():
+            K[nc, (n, n, n)](x, solver.cell_coeff2, y, solver.G, solver.dofmap, D)
+        kname = f"stiffness_kernel<{tname},{n},0,1> (fus_stiffness_{a.dtype})"
+        bytes_stiff = nc * (nd3 * 4 + 6 * nd3 * s + s) + 2 * s * nd  # B_K per cell + 2s per dof
     reps = max(20, a.steps)
     for _ in range(3):
-        K[nc, (n, n, n)](x, solver.cell_coeff2, y, solver.G, solver.dofmap, D)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        launch()
     barrier()
+    e0.record()
+    for _ in range(reps):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    t_stiff = e0.elapsed_time(e1) * 1e-3 / reps
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
     for ea, eb in evs:
         y.zero_()
         ea.record()
-        K[nc, (n, n, n)](x, solver.cell_coeff2, y, solver.G, solver.dofmap, D)
+        launch()
         eb.record()
     torch.cuda.synchronize()
-    t_stiff = float(np.mean([ea.elapsed_time(eb) for ea, eb in evs])) * 1e-3
-    bytes_stiff = nc * (nd3 * 4 + 6 * nd3 * s + s) + 2 * s * nd  # B_K per cell + 2s per dof
+    t_stiff_min = float(np.min([ea.elapsed_time(eb) for ea, eb in evs])) * 1e-3
     peak, peak_kind = peaks()
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "stiffness_traffic.json")))
-        if a.n_per_gpu == tr.get("n_per_gpu") and a.dtype == tr.get("dtype"):
+        if (n_per_gpu == tr.get("n_per_gpu") and a.dtype == tr.get("dtype") and a.workload == "linear_box"
+                and deg == 4 and world == 1):
             traffic = tr["dram_bytes_per_launch"]
     except Exception:
         pass
-    roofline = {"kernel": "stiffness_kernel<double,5> (fus_stiffness_f64)" if a.dtype == "f64" else "stiffness_kernel<float,5>",
-                "bound": "hbm", "achieved": bytes_stiff / t_stiff / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": bytes_stiff / t_stiff / 1e9 / peak, "traffic": traffic, "peak_kind": peak_kind,
-                "algorithmic_bytes_per_launch": bytes_stiff, "launch_ms": t_stiff * 1e3}
+    roofline = {"kernel": kname, "bound": "hbm", "achieved": bytes_stiff / t_stiff / 1e9, "peak": peak,
+                "unit": "GB/s", "frac": bytes_stiff / t_stiff / 1e9 / peak, "traffic": traffic,
+                "peak_kind": peak_kind, "algorithmic_bytes_per_launch": bytes_stiff, "launch_ms": t_stiff * 1e3,
+                "launch_ms_min": t_stiff_min * 1e3, "launches_timed": reps}
     # the mass operator (cells) for the "operators" block
     evm = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
     c1 = torch.ones(nc, dtype=solver.T, device="cuda")
@@ -458,7 +523,7 @@ def main():
 
     line = {
         "metric": "fused RK4 stage throughput (global dofs x stages / s)", "value": value, "unit": "GDoF/s",
-        "n_gpus": world, "steps": a.steps, "warmup": warmup, "ms_per_step": elapsed / a.steps * 1e3,
+        "workload": a.workload, "n_gpus": world, "steps": a.steps, "warmup": warmup, "ms_per_step": elapsed / a.steps * 1e3,
         "steps_per_s": a.steps / elapsed, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": a.dtype, "data": "synthetic", "config": {**config, "global_dofs": gdofs_global,
                                                           "global_cells": list(info["global_cells"])},
@@ -470,11 +535,11 @@ def main():
         "stage_roofline": {"bound": "hbm", "achieved": stage_bytes / stage_t / 1e9, "peak": peak, "unit": "GB/s",
                            "frac": stage_bytes / stage_t / 1e9 / peak,
                            "algorithmic_bytes_per_stage": stage_bytes, "stage_ms": stage_t * 1e3},
-        "operators": {"stiffness_gdofs": info["ndofs_local"] / t_stiff / 1e9, "mass_gdofs": info["ndofs_local"] / t_mass / 1e9,
+        "operators": {("westervelt_stage_kernel_gdofs" if W["nonlinear"] else "stiffness_gdofs"): info["ndofs_local"] / t_stiff / 1e9, "mass_gdofs": info["ndofs_local"] / t_mass / 1e9,
                       "per_gpu_dofs": info["ndofs_local"]},
     }
     if rank == 0:
-        if world == 1 and not a.no_cpu:
+        if world == 1 and not a.no_cpu and a.workload == "linear_box" and deg == P:
             r = time_cpu(3, 1, budget_s=12.0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         else:

@@ -342,6 +342,17 @@ def tensor_dofmap(mesh: BoxMesh, P: int, order: str = "basix") -> np.ndarray:
     return np.ascontiguousarray(dm)
 
 
+def box_cell_colours(mesh: BoxMesh) -> np.ndarray:
+    """The exact 8-colouring of a structured box: colour = parity of the cell's
+    (x, y, z) position (global parity, so it is consistent across parts)."""
+    Nx, Ny, Nz = mesh.ncells
+    ox, oy, oz = mesh.cell_origin
+    cx = (np.arange(Nx) + ox) & 1
+    cy = (np.arange(Ny) + oy) & 1
+    cz = (np.arange(Nz) + oz) & 1
+    return (cx[:, None, None] * 4 + cy[None, :, None] * 2 + cz[None, None, :]).astype(np.int32).ravel()
+
+
 def num_dofs(ncells, P: int) -> int:
     if np.isscalar(ncells):
         ncells = (ncells,) * 3

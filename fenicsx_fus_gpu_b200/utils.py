@@ -157,6 +157,61 @@ def facet_integration_domain(facets, mesh):
     return boundary_data
 
 
+def colour_cells(connectivity, seed: int = 0) -> np.ndarray:
+    """Greedy distance-1 colouring of the cells of a conforming mesh: no two
+    cells of one colour share an entry of ``connectivity``.
+
+    ``connectivity`` is ``(Nc, k)`` int: the geometry dofmap ``x_dofs`` (8
+    vertices per hexahedron - two cells share a dof iff they share a vertex, so
+    this is enough and 16x cheaper at degree 4) or the dofmap itself.  The
+    reference scatters with atomics only (``cuda/operators.py:190``); the
+    colouring backs the deterministic ``FUS_NO_ATOMICS`` launches
+    (``operators.stiffness_operator(..., colour_offsets=...)``).
+
+    Each colour is a maximal independent set grown Luby-style: among the
+    candidates, a cell joins when it holds the highest (seeded, random)
+    priority on every one of its entries; its neighbours leave the candidate
+    set; repeat until no candidate is left, then open the next colour.
+    Vectorised over cells; returns ``(Nc,) int32`` colours ``0..ncolours-1``.
+    """
+    conn = np.ascontiguousarray(connectivity)
+    nc, k = conn.shape
+    colour = np.full(nc, -1, dtype=np.int32)
+    if nc == 0:
+        return colour
+    nnode = int(conn.max()) + 1
+    prio = np.random.default_rng(seed).permutation(nc).astype(np.int64) + 1
+    remaining = np.arange(nc)
+    c = 0
+    while remaining.size:
+        cand = remaining
+        taken = np.zeros(nnode, dtype=bool)  # entries touched by this colour so far
+        while cand.size:
+            dm = conn[cand]
+            pc = prio[cand]
+            best = np.zeros(nnode, dtype=np.int64)
+            np.maximum.at(best, dm.ravel(), np.repeat(pc, k))
+            win = (best[dm] == pc[:, None]).all(axis=1)
+            sel = cand[win]
+            colour[sel] = c
+            taken[conn[sel].ravel()] = True
+            rest = cand[~win]
+            cand = rest[~taken[conn[rest]].any(axis=1)]
+        remaining = remaining[colour[remaining] < 0]
+        c += 1
+    return colour
+
+
+def colour_order(colours):
+    """``(perm, offsets)``: the stable permutation that makes every colour a
+    contiguous block of cells and the block boundaries (``ncolours + 1`` int64).
+    Apply ``perm`` to every per-cell array (dofmap, G, detJ, constants)."""
+    colours = np.asarray(colours)
+    perm = np.argsort(colours, kind="stable")
+    counts = np.bincount(colours, minlength=int(colours.max()) + 1 if colours.size else 0)
+    return perm, np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+
+
 def compute_diffusivity_of_sound(w0: float, c0: float, alpha: float) -> float:
     """``delta = 2 alpha c0^3 / w0^2`` with alpha in dB/m converted to Np/m -
     cuda/utils.py:157-162."""
