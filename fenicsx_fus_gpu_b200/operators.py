@@ -64,7 +64,7 @@ mass_operator = _Mass()
 class _Stiffness(_Kernel):
     """Sum-factorised stiffness action - cuda/operators.py:87-190."""
 
-    def __init__(self, P: int, float_type):
+    def __init__(self, P: int, float_type, colour_offsets=None):
         if not 2 <= int(P) <= 7:
             raise ValueError(f"stiffness_operator: degree {P} not in 2..7")
         self.P = int(P)
@@ -72,6 +72,12 @@ class _Stiffness(_Kernel):
         self.float_type = np.dtype(float_type)
         _lib.sfx(self.float_type)  # validates
         self.flags = 0
+        self.colour_offsets = None
+        if colour_offsets is not None:
+            off = [int(v) for v in colour_offsets]
+            if len(off) < 2 or off[0] != 0 or any(b < a for a, b in zip(off, off[1:])):
+                raise ValueError("stiffness_operator: colour_offsets must be 0 = o_0 <= o_1 <= ... <= ncells")
+            self.colour_offsets = off
 
     def __call__(self, x, entity_constants, y, G_entity, entity_dofmap, dphi):
         T = self.float_type
@@ -96,14 +102,36 @@ class _Stiffness(_Kernel):
             if td.size != self.n**2:
                 raise _lib.FusError("stiffness_operator: dphi must be (n, n)")
             ptr = td.ptr
-        check(fn("fus_stiffness", T)(xd.ptr, cd.ptr, yd.ptr, gd.ptr, dm.ptr, ptr, dm.shape[0],
-                                     self.P, self.flags, current_stream()), "fus_stiffness")
+        f, st = fn("fus_stiffness", T), current_stream()
+        if self.colour_offsets is None:
+            check(f(xd.ptr, cd.ptr, yd.ptr, gd.ptr, dm.ptr, ptr, dm.shape[0], self.P, self.flags, st),
+                  "fus_stiffness")
+            return
+        # deterministic path: the cells are sorted by colour, no two cells of a colour share
+        # a dof, so each colour is one launch with plain read-modify-write instead of atomics
+        off = self.colour_offsets
+        if off[-1] != dm.shape[0]:
+            raise _lib.FusError("stiffness_operator: colour_offsets[-1] must equal the number of cells")
+        s = T.itemsize
+        flags = self.flags | FUS_NO_ATOMICS
+        for a, b in zip(off, off[1:]):
+            if b > a:
+                check(f(xd.ptr, cd.ptr + a * s, yd.ptr, gd.ptr + a * nd3 * 6 * s, dm.ptr + a * nd3 * 4, ptr,
+                        b - a, self.P, flags, st), "fus_stiffness")
+                flags |= FUS_TABLES_RESIDENT  # the derivative table went up with the first colour
 
 
-def stiffness_operator(P, float_type):
+def stiffness_operator(P, float_type, colour_offsets=None):
     """Returns the stiffness kernel for degree ``P`` and ``float_type``
-    (cuda/operators.py:73-192)."""
-    return _Stiffness(P, float_type)
+    (cuda/operators.py:73-192).
+
+    ``colour_offsets`` (optional, not in the reference): the cells have been
+    permuted so that colour ``c`` occupies rows ``colour_offsets[c] :
+    colour_offsets[c+1]`` of every per-cell array (``utils.colour_cells`` /
+    ``utils.colour_order``).  The action then runs one atomics-free launch per
+    colour and its result is bit-reproducible from run to run; the default
+    (atomics) is faster on B200 - see DESIGN.md."""
+    return _Stiffness(P, float_type, colour_offsets)
 
 
 def _vec3(name):

@@ -188,3 +188,39 @@ def test_empty_launch_and_host_arrays_raise(ops):
         ops.axpy[1, 1](1.0, np.zeros(4), np.zeros(4))  # host arrays: no CPU path
     with pytest.raises(ValueError):
         ops.stiffness_operator(8, np.float64)
+
+
+@pytest.mark.parametrize("P,tag,kind", [(2, "f64", "box"), (4, "f64", "greedy"), (4, "f32", "box"), (5, "f64", "greedy"),
+                                        (7, "f32", "greedy")])
+def test_coloured_stiffness_is_exact_and_reproducible(ops, P, tag, kind):
+    """Atomics-free launches over colour classes (FUS_NO_ATOMICS): same result as the
+    oracle, bit-identical from run to run, and equal to the atomic path to rounding."""
+    from fenicsx_fus_gpu_b200 import substrate as S, utils
+    from oracle import oracle as orc
+
+    dt = np.float64 if tag == "f64" else np.float32
+    tb = S.element_tables(P, "basix", dt)
+    mesh = S.create_box((7, 6, 5), (1.0, 0.9, 0.8), dtype=dt, perturb=0.2, seed=11)
+    dofmap = S.tensor_dofmap(mesh, P)
+    nd, Nc, n = int(dofmap.max()) + 1, dofmap.shape[0], P + 1
+    colours = S.box_cell_colours(mesh) if kind == "box" else utils.colour_cells(mesh.x_dofs, seed=1)
+    perm, off = utils.colour_order(colours)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(nd).astype(dt)
+    coeff = rng.uniform(0.5, 2.0, Nc).astype(dt)
+    G = np.zeros((Nc, tb.n**3, 6), dt)
+    orc.compute_scaled_geometrical_factor(G, (mesh.x_dofs, mesh.x_g), Nc, tb.dphi, tb.wts)
+    y_ref = np.zeros(nd, dt)
+    orc.stiffness_operator(P, x, coeff, y_ref, G, dofmap, tb.dphi_1D)
+
+    K = ops.stiffness_operator(P, dt, colour_offsets=off)
+    xd, cd, Gd, dmd = d(x), d(coeff[perm]), d(G[perm]), d(dofmap[perm])
+    runs = []
+    for _ in range(3):
+        y = torch.zeros(nd, dtype=xd.dtype, device="cuda")
+        K[Nc, (n, n, n)](xd, cd, y, Gd, dmd, tb.dphi_1D)
+        runs.append(y.cpu().numpy())
+    assert rel_l2(runs[0], y_ref) < TOL[tag]
+    assert np.array_equal(runs[0], runs[1]) and np.array_equal(runs[0], runs[2])
+    with pytest.raises(Exception):
+        ops.stiffness_operator(P, dt, colour_offsets=[0, Nc - 1])[Nc, (n, n, n)](xd, cd, y, Gd, dmd, tb.dphi_1D)

@@ -210,3 +210,31 @@ def test_diffusivity_of_sound():
     w0, c0, a = 2 * np.pi * 1.1e6, 1480.0, 0.2
     assert utils.compute_diffusivity_of_sound(w0, c0, a) == pytest.approx(
         2 * (a / 20 * np.log(10)) * c0**3 / w0**2, rel=1e-15)
+
+
+@pytest.mark.parametrize("ncells,perturb", [((5, 4, 6), 0.0), ((3, 3, 3), 0.2), ((1, 1, 1), 0.0), ((2, 1, 7), 0.1)])
+def test_cell_colouring_is_a_valid_partition(ncells, perturb):
+    """No two cells of a colour share a dof (checked on the FULL degree-3 dofmap although the
+    colouring only looks at the 8 vertices per cell); the box colouring uses at most 8 colours."""
+    from fenicsx_fus_gpu_b200 import substrate as S, utils
+
+    mesh = S.create_box(ncells, perturb=perturb)
+    dofmap = S.tensor_dofmap(mesh, 3)
+    for colours in (utils.colour_cells(mesh.x_dofs), utils.colour_cells(mesh.x_dofs, seed=7),
+                    S.box_cell_colours(mesh), utils.colour_cells(dofmap)):
+        assert colours.shape == (mesh.num_cells,) and colours.min() >= 0
+        for c in range(int(colours.max()) + 1):
+            touched = dofmap[colours == c].ravel()
+            assert np.unique(touched).size == touched.size
+        perm, off = utils.colour_order(colours)
+        assert off[0] == 0 and off[-1] == mesh.num_cells and np.all(np.diff(colours[perm]) >= 0)
+        assert np.array_equal(np.sort(perm), np.arange(mesh.num_cells))
+    assert S.box_cell_colours(mesh).max() < 8
+    # colours of a part agree with the colours of the same cells in the whole box
+    parts = S.partition_box((4, 4, 4), 2, 8)
+    whole = S.box_cell_colours(S.create_box((4, 4, 4))).reshape(4, 4, 4)
+    for p in parts:
+        o, n = p.mesh.cell_origin, p.mesh.ncells
+        assert np.array_equal(S.box_cell_colours(p.mesh).reshape(n),
+                              whole[o[0]:o[0] + n[0], o[1]:o[1] + n[1], o[2]:o[2] + n[2]])
+    assert utils.colour_cells(np.zeros((0, 8), np.int32)).size == 0

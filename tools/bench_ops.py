@@ -84,6 +84,18 @@ def main():
         if op == "stiffness":
             f = lambda: K[Nc, (n, n, n)](x, c, y, G, dofmap, D)  # noqa: E731
             bytes_ = Nc * (Nd * 4 + 6 * Nd * s + s) + 2 * s * nd
+        elif op in ("coloured", "coloured_greedy"):
+            # the same action as one atomics-free launch per colour (8 colours on a box; the
+            # greedy colouring of an unstructured mesh needs more): bit-reproducible, and the
+            # evidence behind "atomics are faster on B200" in DESIGN.md
+            from fenicsx_fus_gpu_b200 import utils
+            col = S.box_cell_colours(mesh) if op == "coloured" else utils.colour_cells(mesh.x_dofs)
+            perm, off = utils.colour_order(col)
+            pt = torch.from_numpy(perm).cuda()
+            Gp, dmp = G[pt].contiguous(), dofmap[pt].contiguous()
+            Kc = ops.stiffness_operator(P, dt, colour_offsets=off)
+            f = lambda: Kc[Nc, (n, n, n)](x, c, y, Gp, dmp, D)  # noqa: E731
+            bytes_ = Nc * (Nd * 4 + 6 * Nd * s + s) + 2 * s * nd
         elif op == "mass":
             f = lambda: ops.mass_operator[1, 128](x, c, y, detJ, dofmap)  # noqa: E731
             bytes_ = Nc * (Nd * (4 + s) + s) + 2 * s * nd
