@@ -138,6 +138,7 @@ class _RK4:
         self._opened = False
         self._bdofs = None
         self._src = self._src2 = self._absb = None
+        self.probe = None  # list: (start, stop) CUDA events around every stage-kernel launch (eager mode)
 
     # ---- set-up helpers ------------------------------------------------------
     def _set_tables(self):
@@ -170,6 +171,19 @@ class _RK4:
             setattr(self, "_" + slot, tmp[idx].contiguous())
 
     # ---- stage pieces --------------------------------------------------------
+    def _probed(self, launch):
+        """Run ``launch()``; with ``self.probe`` a list (eager mode only), bracket it with CUDA
+        events on the launching stream so a benchmark can read the kernel's duration in situ."""
+        if self.probe is None:
+            launch()
+            return
+        torch = _torch()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        launch()
+        e1.record()
+        self.probe.append((e0, e1))
+
     def _ptr(self, t):
         return None if t is None else t.data_ptr()
 
@@ -382,10 +396,10 @@ class LinearSpectral3D(_RK4):
 
     def _assemble(self, stage, g, dg, use_table):
         # b += K(-1/rho; un)                                  (cuda/demo_linear_box.py:543-545)
-        check(fn("fus_stiffness", self.dtype)(
+        self._probed(lambda: check(fn("fus_stiffness", self.dtype)(
             self.un.data_ptr(), self.cell_coeff2.data_ptr(), self.b.data_ptr(), self.G.data_ptr(),
             self.dofmap.data_ptr(), None, self.ncells, self.P, FUS_TABLES_RESIDENT, current_stream()),
-            "fus_stiffness")
+            "fus_stiffness"))
         # b += g * src + vn * absb                            (:546-551)
         self._boundary(stage, g, dg, use_table)
 
@@ -452,11 +466,11 @@ class WesterveltSpectral3D(_RK4):
     def _assemble(self, stage, g, dg, use_table):
         # b += K(c3; un) + K(c4; vn) + M(c5; vn^2) and m += M(c2; un): ONE pass over G, detJ
         # and the dofmap, un / vn gathered once                    (:609-612, :620-628)
-        check(fn("fus_stiffness_westervelt", self.dtype)(
+        self._probed(lambda: check(fn("fus_stiffness_westervelt", self.dtype)(
             self.un.data_ptr(), self.c3.data_ptr(), self.ku.data_ptr(), self.c4.data_ptr(),
             self.c2.data_ptr(), self.c5.data_ptr(), self.m.data_ptr(), self.b.data_ptr(),
             self.G.data_ptr(), self.detJ.data_ptr(), self.dofmap.data_ptr(), None, self.ncells, self.P,
-            FUS_TABLES_RESIDENT, current_stream()), "fus_stiffness_westervelt")
+            FUS_TABLES_RESIDENT, current_stream()), "fus_stiffness_westervelt"))
         # b += g*src + dg*src2 + vn*absb                                      (:629-639)
         self._boundary(stage, g, dg, use_table)
 
