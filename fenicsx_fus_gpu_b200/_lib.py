@@ -29,6 +29,9 @@ def _sigs():
         "fus_stiffness": [P, P, P, P, P, P, L, I, I, P],
         "fus_stiffness2": [P, P, P, P, P, P, P, P, L, I, I, P],
         "fus_stiffness_westervelt": [P, P, P, P, P, P, P, P, P, P, P, P, L, I, I, P],
+        "fus_stiffness_affine": [P, P, P, P, P, P, P, L, I, I, P],
+        "fus_stiffness_westervelt_affine": [P, P, P, P, P, P, P, P, P, P, P, P, P, L, I, I, P],
+        "fus_compress_geometry": [P, P, P, P, P, P, L, I, T, P],
         "fus_mass": [P, P, P, P, P, L, I, P],
         "fus_axpy": [T, P, P, L, P],
         "fus_copy": [P, P, L, P],

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libfus_b200.so")
-SOURCES = ["api.cu", "stiffness.cu", "mass.cu", "vector.cu", "rk.cu", "geometry.cu", "halo.cu"]
+SOURCES = ["api.cu", "stiffness.cu", "stiffness_affine.cu", "mass.cu", "vector.cu", "rk.cu", "geometry.cu", "halo.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 EXTRA = os.environ.get("FUS_NVCC_EXTRA", "").split()  # experiments, e.g. -DFUS_CFG_ALT
 # IEEE division / sqrt (no fast-math): parity with the reference is rel-L2 <= 1e-12 in f64
@@ -29,7 +29,7 @@ FLAGS = [
 
 
 def _deps(src: str):
-    d = [os.path.join(CSRC, src), os.path.join(CSRC, "fus_common.cuh"),
+    d = [os.path.join(CSRC, src), os.path.join(CSRC, "fus_common.cuh"), os.path.join(CSRC, "stiffness_kernel.cuh"),
          os.path.join(os.path.dirname(HERE), "include", "fus_b200.h"), os.path.abspath(__file__)]
     return [p for p in d if os.path.exists(p)]
 

@@ -25,6 +25,10 @@ void fus_count_launch(int n = 1);
 
 int fus_num_sms();
 
+// stiffness_affine.cu keeps its own copy of the derivative tables (fus_set_dphi_* fills both)
+int fus_affine_set_dphi_f64(int P, const double* dphi, void* stream);
+int fus_affine_set_dphi_f32(int P, const float* dphi, void* stream);
+
 // ---- device-side PTX wrappers ---------------------------------------------
 #ifdef __CUDACC__
 

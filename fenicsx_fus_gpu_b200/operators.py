@@ -134,6 +134,39 @@ def stiffness_operator(P, float_type, colour_offsets=None):
     return _Stiffness(P, float_type, colour_offsets)
 
 
+class _StiffnessAffine(_Kernel):
+    """The stiffness action on cells with a constant Jacobian: ``G[c, q, :] = weights[q] *
+    Gc[c, :]`` (``precompute.compress_geometry``), so only 6 factors per cell are read."""
+
+    def __init__(self, P: int, float_type):
+        if not 2 <= int(P) <= 7:
+            raise ValueError(f"stiffness_operator_affine: degree {P} not in 2..7")
+        self.P, self.n, self.float_type = int(P), int(P) + 1, np.dtype(float_type)
+        _lib.sfx(self.float_type)
+
+    def __call__(self, x, entity_constants, y, Gc, weights, entity_dofmap, dphi):
+        T = self.float_type
+        xd, yd, cd, gd, wd = dev(x, T), dev(y, T), dev(entity_constants, T), dev(Gc, T), dev(weights, T)
+        dm = dev(entity_dofmap, np.int32)
+        nd3 = self.n**3
+        if len(dm.shape) != 2 or dm.shape[1] != nd3:
+            raise _lib.FusError(f"stiffness_operator_affine: dofmap must be (ncells, {nd3}), got {dm.shape}")
+        if gd.size != dm.shape[0] * 6 or cd.size != dm.shape[0] or wd.size != nd3:
+            raise _lib.FusError("stiffness_operator_affine: Gc (ncells, 6), constants (ncells,), weights (n^3,)")
+        if dm.shape[0] == 0:
+            raise ValueError("stiffness_operator_affine: zero cells (empty launch)")
+        tab = np.ascontiguousarray(dphi, dtype=T) if isinstance(dphi, np.ndarray) else None
+        ptr = tab.ctypes.data if tab is not None else dev(dphi, T).ptr
+        check(fn("fus_stiffness_affine", T)(xd.ptr, cd.ptr, yd.ptr, gd.ptr, wd.ptr, dm.ptr, ptr, dm.shape[0],
+                                            self.P, 0, current_stream()), "fus_stiffness_affine")
+
+
+def stiffness_operator_affine(P, float_type):
+    """Stiffness kernel for affine cells (not in the reference):
+    ``k[grid, block](x, constants, y, Gc, weights, dofmap, dphi)``."""
+    return _StiffnessAffine(P, float_type)
+
+
 def _vec3(name):
     class K(_Kernel):
         def __call__(self, a, b, c):

@@ -121,3 +121,37 @@ def compute_boundary_facets_scaled_jacobian_determinant(detJ_f, mesh, boundary_d
         check(fn("fus_facet_geometry", T)(_ptr(buf), _ptr(xd), _ptr(xg), _ptr(bd), _ptr(dp), _ptr(w),
                                           nf, nq, current_stream()), "fus_facet_geometry")
     _finish(buf, host)
+
+
+def compress_geometry(G, detJ, weights, tol=None):
+    """Affine-cell detection and compression (not in the reference).
+
+    On a cell with a constant Jacobian the tables of cuda/precompute.py:76-163
+    factor as ``G[c, q, :] = weights[q] * Gc[c, :]`` and ``detJ[c, q] = weights[q]
+    * detJc[c]``.  Returns ``(affine, Gc, detJc)`` as device tensors: ``affine``
+    (Nc,) int32 is 1 where every weight-normalised record of the cell lies within
+    ``tol`` (relative; default 2048 machine epsilons = 4.5e-13 in float64 - the tables of an
+    exactly affine cell carry rounding noise of ~N eps from ``dphi @ coords`` on an N^3 box,
+    350 eps at N = 250) of the cell mean, ``Gc``
+    (Nc, 6) and ``detJc`` (Nc,) are those means.  ``detJ`` may be None.
+    ``G`` / ``detJ`` / ``weights`` are device arrays or numpy (uploaded)."""
+    import torch
+
+    Gd, _ = _to_dev(G, G.dtype) if isinstance(G, np.ndarray) else (G, False)
+    T = _lib.dev(Gd).dtype
+    tdt = torch.float64 if T == np.float64 else torch.float32
+    w, _ = _to_dev(weights, T)
+    nq = int(_lib.dev(w).size)
+    nc = int(_lib.dev(Gd).size // (6 * nq))
+    Jd = None
+    if detJ is not None:
+        Jd, _ = _to_dev(detJ, T)
+    if tol is None:
+        tol = 2048.0 * float(np.finfo(T).eps)
+    Gc = torch.empty((nc, 6), dtype=tdt, device="cuda")
+    detJc = torch.empty((nc,), dtype=tdt, device="cuda")
+    affine = torch.zeros((nc,), dtype=torch.int32, device="cuda")
+    check(fn("fus_compress_geometry", T)(_ptr(Gd), None if Jd is None else _ptr(Jd), _ptr(w), _ptr(Gc),
+                                         _ptr(detJc) if Jd is not None else None, _ptr(affine), nc, nq,
+                                         float(tol), current_stream()), "fus_compress_geometry")
+    return affine, Gc, detJc

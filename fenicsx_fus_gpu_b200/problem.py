@@ -142,6 +142,8 @@ def linear_solver(su: Setup, source_facets, absorbing_facets, rho=1000.0, c0=150
                   p0=60000.0, source_predicate=None, absorbing_predicate=None, **kw) -> LinearSpectral3D:
     """cuda/demo_linear_box.py:336-345 coefficients + the fused solver."""
     nc = su.mesh.num_cells
+    if kw.get("geometry") == "auto":
+        kw.setdefault("weights", su.tables.wts)
     fd1, dJ1, bd1 = facet_group(su, source_facets, source_predicate)
     fd2, dJ2, bd2 = facet_group(su, absorbing_facets, absorbing_predicate)
     return LinearSpectral3D(
@@ -159,6 +161,8 @@ def westervelt_solver(su: Setup, source_facets, absorbing_facets, rho=1000.0, c0
         p0 = rho * c0 * 0.38557513826589934  # source velocity of the bowl demo (:66-67)
     delta = utils.compute_diffusivity_of_sound(2.0 * np.pi * f0, c0, alpha_dB)
     nc = su.mesh.num_cells
+    if kw.get("geometry") == "auto":
+        kw.setdefault("weights", su.tables.wts)
     fd1, dJ1, bd1 = facet_group(su, source_facets, source_predicate)
     fd2, dJ2, bd2 = facet_group(su, absorbing_facets, absorbing_predicate)
     n1, n2 = bd1.shape[0], bd2.shape[0]

@@ -95,7 +95,7 @@ class _RK4:
     westervelt = False
 
     def __init__(self, P, float_type, ndofs, dofmap, G, dphi_1D, halo=None, source=None,
-                 source_at_stage_time=True, use_graph=True):
+                 source_at_stage_time=True, use_graph=True, geometry="stream", weights=None):
         torch = _torch()
         if not torch.cuda.is_available():
             raise _lib.FusError("no CUDA device: this package has no CPU path")
@@ -139,6 +139,17 @@ class _RK4:
         self._bdofs = None
         self._src = self._src2 = self._absb = None
         self.probe = None  # list: (start, stop) CUDA events around every stage-kernel launch (eager mode)
+        # geometry = "stream": G (and detJ) are read in full every stage, as the reference does;
+        # "auto": cells whose Jacobian is constant (precompute.compress_geometry) keep 6 (+1)
+        # values instead of 6 (+1) n^3 and go through the affine kernels, the others are streamed
+        if geometry not in ("stream", "auto"):
+            raise ValueError("geometry must be 'stream' or 'auto'")
+        if geometry == "auto" and weights is None:
+            raise ValueError("geometry='auto' needs the quadrature weights (n^3,)")
+        self.geometry = geometry
+        self._weights = None if weights is None else _dev(weights, self.T)
+        self.naff = 0  # cells [0, naff) are affine (after the set-up permutation)
+        self.Gc = self.detJc = None
 
     # ---- set-up helpers ------------------------------------------------------
     def _set_tables(self):
@@ -169,6 +180,40 @@ class _RK4:
             tmp = torch.zeros(self.ndofs, dtype=self.T, device="cuda")
             self._mass(ones, coeff, tmp, dJ, bdm)
             setattr(self, "_" + slot, tmp[idx].contiguous())
+
+    def _setup_geometry(self, detJ, cell_arrays):
+        """geometry='auto': classify the cells, move the affine ones to the front of every
+        per-cell array (``cell_arrays``: attribute names of (Nc,) / (Nc, n^3) tensors; the dofmap
+        and G are handled here), keep G / detJ for the remaining cells only.  Summation order
+        inside the atomics aside, a cell permutation does not change the result."""
+        if self.geometry != "auto" or self.ncells == 0:
+            return
+        torch = _torch()
+        from . import precompute as pre
+
+        affine, Gc, detJc = pre.compress_geometry(self.G, detJ, self._weights)
+        na = int(affine.sum().item())
+        nc = self.ncells
+        self.naff = na
+        if na == 0:
+            return
+        if na < nc:
+            perm = torch.argsort(1 - affine, stable=True)  # affine cells first, original order kept
+            self.cell_perm = perm
+            self.dofmap = self.dofmap[perm].contiguous()
+            for name in cell_arrays:
+                setattr(self, name, getattr(self, name)[perm].contiguous())
+            Gc, detJc = Gc[perm], detJc[perm]
+            rest = perm[na:]
+            self.G = self.G[rest].contiguous()
+            if detJ is not None:
+                self.detJ = detJ[rest].contiguous()
+        else:
+            self.G = None  # nothing left to stream (the caller's tensor is not touched)
+            if detJ is not None:
+                self.detJ = None
+        self.Gc = Gc[:na].contiguous()
+        self.detJc = detJc[:na].contiguous() if detJ is not None else None
 
     # ---- stage pieces --------------------------------------------------------
     def _probed(self, launch):
@@ -355,7 +400,8 @@ class _RK4:
     def stage_bytes(self):
         s = self.dtype.itemsize
         Nd = self.n**3
-        stiff = self.ncells * (Nd * 4 + 6 * Nd * s + s) + 2 * s * self.ndofs
+        nstream = self.ncells - self.naff
+        stiff = nstream * (Nd * 4 + 6 * Nd * s + s) + self.naff * (Nd * 4 + 7 * s) + 2 * s * self.ndofs
         return stiff + 14 * s * self.ndofs
 
 
@@ -372,9 +418,9 @@ class LinearSpectral3D(_RK4):
     def __init__(self, P, float_type, ndofs, dofmap, G, detJ, dphi_1D, cell_coeff1, cell_coeff2,
                  bfacet_dofmap1=None, detJ_f1=None, facet_coeff1=None, bfacet_dofmap2=None,
                  detJ_f2=None, facet_coeff2=None, halo=None, source=None,
-                 source_at_stage_time=True, use_graph=True):
+                 source_at_stage_time=True, use_graph=True, geometry="stream", weights=None):
         super().__init__(P, float_type, ndofs, dofmap, G, dphi_1D, halo, source,
-                         source_at_stage_time, use_graph)
+                         source_at_stage_time, use_graph, geometry, weights)
         torch = _torch()
         self.cell_coeff2 = _dev(cell_coeff2, self.T)
         c1 = _dev(cell_coeff1, self.T)
@@ -393,13 +439,24 @@ class LinearSpectral3D(_RK4):
         if bd2.shape[0]:
             terms.append(("absb", bd2, _dev(detJ_f2, self.T), _dev(facet_coeff2, self.T)))
         self._boundary_setup(terms)
+        self._setup_geometry(None, ["cell_coeff2"])
+
+    def _stiffness(self):
+        na, nc, st = self.naff, self.ncells, current_stream()
+        if na:  # affine cells: 6 factors per cell, nothing streamed but the dofmap
+            check(fn("fus_stiffness_affine", self.dtype)(
+                self.un.data_ptr(), self.cell_coeff2.data_ptr(), self.b.data_ptr(), self.Gc.data_ptr(),
+                self._weights.data_ptr(), self.dofmap.data_ptr(), None, na, self.P, FUS_TABLES_RESIDENT, st),
+                "fus_stiffness_affine")
+        if na < nc:
+            check(fn("fus_stiffness", self.dtype)(
+                self.un.data_ptr(), self.cell_coeff2[na:].data_ptr(), self.b.data_ptr(), self.G.data_ptr(),
+                self.dofmap[na:].data_ptr(), None, nc - na, self.P, FUS_TABLES_RESIDENT, st),
+                "fus_stiffness")
 
     def _assemble(self, stage, g, dg, use_table):
         # b += K(-1/rho; un)                                  (cuda/demo_linear_box.py:543-545)
-        self._probed(lambda: check(fn("fus_stiffness", self.dtype)(
-            self.un.data_ptr(), self.cell_coeff2.data_ptr(), self.b.data_ptr(), self.G.data_ptr(),
-            self.dofmap.data_ptr(), None, self.ncells, self.P, FUS_TABLES_RESIDENT, current_stream()),
-            "fus_stiffness"))
+        self._probed(self._stiffness)
         # b += g * src + vn * absb                            (:546-551)
         self._boundary(stage, g, dg, use_table)
 
@@ -431,9 +488,9 @@ class WesterveltSpectral3D(_RK4):
                  cell_coeff3, cell_coeff4, cell_coeff5, bfacet_dofmap1=None, detJ_f1=None,
                  facet_coeff1_1=None, facet_coeff2_1=None, bfacet_dofmap2=None, detJ_f2=None,
                  facet_coeff1_2=None, facet_coeff2_2=None, halo=None, source=None,
-                 source_at_stage_time=True, use_graph=True):
+                 source_at_stage_time=True, use_graph=True, geometry="stream", weights=None):
         super().__init__(P, float_type, ndofs, dofmap, G, dphi_1D, halo, source,
-                         source_at_stage_time, use_graph)
+                         source_at_stage_time, use_graph, geometry, weights)
         torch = _torch()
         self.detJ = _dev(detJ, self.T)
         self.c2, self.c3 = _dev(cell_coeff2, self.T), _dev(cell_coeff3, self.T)
@@ -459,6 +516,7 @@ class WesterveltSpectral3D(_RK4):
             terms.append(("absb", bd2, _dev(detJ_f2, self.T), _dev(facet_coeff2_2, self.T)))
         self._boundary_setup(terms)
         self.m.zero_()  # state-dependent part, accumulated per stage, zeroed by the close kernel
+        self._setup_geometry(self.detJ, ["c2", "c3", "c4", "c5"])
 
     def _state(self):
         return super()._state() + [self.m0]
@@ -466,13 +524,24 @@ class WesterveltSpectral3D(_RK4):
     def _assemble(self, stage, g, dg, use_table):
         # b += K(c3; un) + K(c4; vn) + M(c5; vn^2) and m += M(c2; un): ONE pass over G, detJ
         # and the dofmap, un / vn gathered once                    (:609-612, :620-628)
-        self._probed(lambda: check(fn("fus_stiffness_westervelt", self.dtype)(
-            self.un.data_ptr(), self.c3.data_ptr(), self.ku.data_ptr(), self.c4.data_ptr(),
-            self.c2.data_ptr(), self.c5.data_ptr(), self.m.data_ptr(), self.b.data_ptr(),
-            self.G.data_ptr(), self.detJ.data_ptr(), self.dofmap.data_ptr(), None, self.ncells, self.P,
-            FUS_TABLES_RESIDENT, current_stream()), "fus_stiffness_westervelt"))
+        self._probed(self._stage_kernel)
         # b += g*src + dg*src2 + vn*absb                                      (:629-639)
         self._boundary(stage, g, dg, use_table)
+
+    def _stage_kernel(self):
+        na, nc, st = self.naff, self.ncells, current_stream()
+        if na:
+            check(fn("fus_stiffness_westervelt_affine", self.dtype)(
+                self.un.data_ptr(), self.c3.data_ptr(), self.ku.data_ptr(), self.c4.data_ptr(),
+                self.c2.data_ptr(), self.c5.data_ptr(), self.m.data_ptr(), self.b.data_ptr(),
+                self.Gc.data_ptr(), self.detJc.data_ptr(), self._weights.data_ptr(), self.dofmap.data_ptr(),
+                None, na, self.P, FUS_TABLES_RESIDENT, st), "fus_stiffness_westervelt_affine")
+        if na < nc:
+            check(fn("fus_stiffness_westervelt", self.dtype)(
+                self.un.data_ptr(), self.c3[na:].data_ptr(), self.ku.data_ptr(), self.c4[na:].data_ptr(),
+                self.c2[na:].data_ptr(), self.c5[na:].data_ptr(), self.m.data_ptr(), self.b.data_ptr(),
+                self.G.data_ptr(), self.detJ.data_ptr(), self.dofmap[na:].data_ptr(), None, nc - na, self.P,
+                FUS_TABLES_RESIDENT, st), "fus_stiffness_westervelt")
 
     def _close(self, stage, dt, count_step):
         last = stage == 3
@@ -486,4 +555,4 @@ class WesterveltSpectral3D(_RK4):
     def stage_bytes(self):
         s = self.dtype.itemsize
         Nd = self.n**3
-        return super().stage_bytes() + self.ncells * Nd * (4 + s) + 6 * s * self.ndofs
+        return super().stage_bytes() + (self.ncells - self.naff) * Nd * s + 6 * s * self.ndofs

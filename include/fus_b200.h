@@ -100,6 +100,43 @@ int fus_stiffness_westervelt_f32(const float* un, const float* c3, const float* 
                                  const float* G, const float* detJ, const int32_t* dofmap,
                                  const float* dphi, int64_t ncells, int P, int flags, void* stream);
 
+/* Affine-cell variants (no counterpart in the reference, which always streams the full
+ * G of cuda/precompute.py:116-163).  On a cell with a constant Jacobian (parallelepiped:
+ * every cell of the box demos) the tables factor exactly,
+ *   G[c, q, :] = wq[q] * Gc[c, :]      detJ[c, q] = wq[q] * detJc[c],
+ * wq (n^3) being the tensor quadrature weights, so a launch reads 6 (7) values per cell
+ * instead of 6 (7) n^3.  Same arithmetic as fus_stiffness_* / fus_stiffness_westervelt_* with
+ * the product wq[q] * Gc formed in registers; results agree with the streamed kernels to
+ * rounding.  Gc: (ncells, 6), detJc: (ncells,), wq: (n^3,) in quadrature order q = i n^2 + j n + k
+ * (fus_compress_geometry_* builds them from G and says which cells qualify). */
+int fus_stiffness_affine_f64(const double* x, const double* coeff, double* y, const double* Gc,
+                             const double* wq, const int32_t* dofmap, const double* dphi,
+                             int64_t ncells, int P, int flags, void* stream);
+int fus_stiffness_affine_f32(const float* x, const float* coeff, float* y, const float* Gc,
+                             const float* wq, const int32_t* dofmap, const float* dphi,
+                             int64_t ncells, int P, int flags, void* stream);
+int fus_stiffness_westervelt_affine_f64(const double* un, const double* c3, const double* vn,
+                                        const double* c4, const double* c2, const double* c5,
+                                        double* m, double* b, const double* Gc,
+                                        const double* detJc, const double* wq,
+                                        const int32_t* dofmap, const double* dphi, int64_t ncells,
+                                        int P, int flags, void* stream);
+int fus_stiffness_westervelt_affine_f32(const float* un, const float* c3, const float* vn,
+                                        const float* c4, const float* c2, const float* c5, float* m,
+                                        float* b, const float* Gc, const float* detJc,
+                                        const float* wq, const int32_t* dofmap, const float* dphi,
+                                        int64_t ncells, int P, int flags, void* stream);
+
+/* Per cell: Gc[c,:] = mean_q G[c,q,:] / wq[q], detJc[c] = mean_q detJ[c,q] / wq[q] (detJ may be
+ * NULL) and affine[c] = 1 when every G[c,q,:] / wq[q] (and detJ[c,q] / wq[q]) lies within
+ * tol * max|Gc[c,:]| (tol * |detJc[c]|) of that mean, else 0.  One CTA per cell. */
+int fus_compress_geometry_f64(const double* G, const double* detJ, const double* wq, double* Gc,
+                              double* detJc, int32_t* affine, int64_t ncells, int nq, double tol,
+                              void* stream);
+int fus_compress_geometry_f32(const float* G, const float* detJ, const float* wq, float* Gc,
+                              float* detJc, int32_t* affine, int64_t ncells, int nq, float tol,
+                              void* stream);
+
 /* Mass (diagonal) action on cells or boundary facets
  *   y[dm[e,i]] += x[dm[e,i]] * detJ[e,i] * coeff[e]
  * Replaces `mass_operator[grid, block](x, coeff, y, detJ, dofmap)` -

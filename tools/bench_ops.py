@@ -96,6 +96,14 @@ def main():
             Kc = ops.stiffness_operator(P, dt, colour_offsets=off)
             f = lambda: Kc[Nc, (n, n, n)](x, c, y, Gp, dmp, D)  # noqa: E731
             bytes_ = Nc * (Nd * 4 + 6 * Nd * s + s) + 2 * s * nd
+        elif op == "affine":
+            # affine cells: 6 factors per cell instead of 6 n^3 (fus_stiffness_affine)
+            aff, Gc, _ = pre.compress_geometry(G, None, torch.from_numpy(tb.wts).cuda())
+            assert bool(aff.all()), "mesh has non-affine cells (use --perturb 0)"
+            Ka = ops.stiffness_operator_affine(P, dt)
+            wq = torch.from_numpy(tb.wts).cuda()
+            f = lambda: Ka[Nc, (n, n, n)](x, c, y, Gc, wq, dofmap, D)  # noqa: E731
+            bytes_ = Nc * (Nd * 4 + 7 * s) + 2 * s * nd
         elif op == "mass":
             f = lambda: ops.mass_operator[1, 128](x, c, y, detJ, dofmap)  # noqa: E731
             bytes_ = Nc * (Nd * (4 + s) + s) + 2 * s * nd
@@ -108,14 +116,15 @@ def main():
             f = lambda: cl(u_.data_ptr(), v_.data_ptr(), u0_.data_ptr(), v0_.data_ptr(), ku_.data_ptr(), None,  # noqa: E731
                            un_.data_ptr(), b_.data_ptr(), m.data_ptr(), 1e-9, 0.5e-9, 1, nd, None, current_stream())
             bytes_ = 12 * s * nd
-        elif op in ("wstage", "lstage"):
+        elif op in ("wstage", "lstage", "wstage_auto", "lstage_auto"):
             from fenicsx_fus_gpu_b200 import problem
             su = problem.box_setup(P, N, 0.0015 * N, dt)
-            if op == "wstage":
-                sol = problem.westervelt_solver(su, [2], [0, 1, 2, 3, 4, 5], p0=1e5)
+            geo = "auto" if op.endswith("_auto") else "stream"
+            if op.startswith("wstage"):
+                sol = problem.westervelt_solver(su, [2], [0, 1, 2, 3, 4, 5], p0=1e5, geometry=geo)
                 dtm = problem.cfl_time_step(P, su.h, 1480.0, 1.1e6, 0.4)
             else:
-                sol = problem.linear_solver(su, [2], [3])
+                sol = problem.linear_solver(su, [2], [3], geometry=geo)
                 dtm = problem.cfl_time_step(P, su.h, 1500.0, 0.5e6, 0.65)
             sol.init()
             sol.rk4(0.0, dtm, 3)
