@@ -31,10 +31,50 @@ def parser(desc, degree, cells):
     ap.add_argument("--cells", type=int, default=cells, help="cells per direction PER GPU (default: the reference demo's mesh)")
     ap.add_argument("--steps", type=int, default=0, help="number of steps (default: run to the demo's final time)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--geometry", default="stream", choices=["stream", "auto"],
+                    help="auto: affine cells keep 6 geometric factors instead of 6 n^3 (same results to rounding)")
+    ap.add_argument("--sample-dir", default=None,
+                    help="write pressure_field_<k>.txt dumps of the sampling plane here (device-side sampling)")
     return ap
 
 
-def run(solver, t0, dt, nsteps, rank, report=100):
+class PlaneSampler:
+    """The reference's "Collect data" block (cuda/demo_linear_piston.py:555-582): once
+    ``t > t_from``, every step for ``ndumps`` steps, the field on the sampling points goes
+    to ``pressure_field_<k>.txt`` as rows ``x, z, p``.  The reference copies the whole
+    vector to the host and evaluates there; here one kernel samples on the device and only
+    the sampled values are copied."""
+
+    def __init__(self, evaluator, coords2, t_from, ndumps, out_dir, rank):
+        self.ev, self.t_from, self.ndumps, self.k = evaluator, t_from, ndumps, 0
+        self.data = None
+        self.dir, self.rank = out_dir, rank
+        if evaluator.npts:
+            import numpy as np
+
+            self.data = np.zeros((evaluator.npts, 3))
+            self.data[:, :2] = coords2
+        os.makedirs(out_dir, exist_ok=True)
+
+    def active(self, t):
+        return t > self.t_from and self.k < self.ndumps
+
+    def dump(self, solver):
+        import numpy as np
+
+        # between steps un == u on the owned dofs (the close kernel opens the next step); its ghost
+        # entries are made current by the stage's own forward halo - scatter_fwd(u_n_d) in the
+        # reference (:566).  Collective: every rank dumps at the same steps.
+        if solver.halo is not None:
+            solver.halo.forward(solver.un, solver.ku)
+        if self.data is not None:
+            self.data[:, 2] = self.ev.to_host(solver.un)
+            with open(os.path.join(self.dir, f"pressure_field_{self.k}_rank{self.rank}.txt"), "a") as f:
+                np.savetxt(f, self.data, fmt="%.8f", delimiter=",")
+        self.k += 1
+
+
+def run(solver, t0, dt, nsteps, rank, report=100, sampler=None):
     """The demos' loop: print u[0] every ``report`` steps (cuda/demo_linear_box.py:569-570),
     then "Solve time" / "Solve time per step" (:579-581)."""
     import torch
@@ -44,9 +84,20 @@ def run(solver, t0, dt, nsteps, rank, report=100):
     t_start = time.perf_counter()
     done = 0
     while done < nsteps:
-        k = min(report, nsteps - done)
+        k = min(report - done % report, nsteps - done)
+        if sampler is not None and sampler.k < sampler.ndumps:
+            # stop at the first step of the sampling window, then go step by step through it
+            t_next = solver.t if done else t0
+            if sampler.active(t_next + dt):
+                k = 1
+            elif sampler.t_from > t_next:
+                k = max(1, min(k, int((sampler.t_from - t_next) / dt)))
         solver.rk4(solver.t if done else t0, dt, k)
         done += k
+        if sampler is not None and sampler.active(solver.t):
+            sampler.dump(solver)
+        if done % report and done < nsteps:
+            continue
         u0 = float(solver.u[0])  # device -> host read of one value (synchronises)
         if rank == 0:
             print(f"t: {solver.t:5.5},\t Steps: {done}/{nsteps}, \t u[0] = {u0}", flush=True)

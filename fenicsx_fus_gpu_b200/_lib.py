@@ -53,6 +53,7 @@ def _sigs():
         "fus_westervelt_mass": [P, P, P, P, P, P, P, P, L, I, P],
         "fus_geometry": [P, P, P, P, P, P, L, I, P],
         "fus_facet_geometry": [P, P, P, P, P, P, L, I, P],
+        "fus_eval_points": [P, P, P, P, P, L, I, P],
         "fus_stiffness_host": [P, P, L, P, P, P, P, P, P, L, I, I, P],
     }
     return s

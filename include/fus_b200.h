@@ -300,6 +300,19 @@ int fus_facet_geometry_f32(float* detJ_f, const int32_t* x_dofs, const float* x_
                            int64_t nf, int nq_f, void* stream);
 
 /* --------------------------------------------------------------------- *
+ * Field sampling (output path)
+ * --------------------------------------------------------------------- */
+
+/* out[p] = sum_{ijk} phi[p,0,i] phi[p,1,j] phi[p,2,k] u[dofmap[cells[p], i n^2 + j n + k]],
+ * phi: (npts, 3, n) 1-D Lagrange values at the points' reference coordinates.  Replaces
+ * `u_n_d.copy_to_host(u_n); u_n_.eval(x_eval, cell_eval)` of
+ * cuda/demo_linear_piston.py:564-570 - the whole vector no longer crosses PCIe per dump. */
+int fus_eval_points_f64(const double* u, const int32_t* dofmap, const int32_t* cells,
+                        const double* phi, double* out, int64_t npts, int P, void* stream);
+int fus_eval_points_f32(const float* u, const int32_t* dofmap, const int32_t* cells,
+                        const float* phi, float* out, int64_t npts, int P, void* stream);
+
+/* --------------------------------------------------------------------- *
  * Host-buffer entry points (the end-to-end path: host <-> device copies are
  * inside the call).  x_host / y_host are HOST pointers (pinned for full
  * speed); every other pointer is a device pointer as above.

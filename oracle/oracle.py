@@ -500,3 +500,14 @@ def rel_l2(a, b) -> float:
     b = np.asarray(b, dtype=np.float64)
     nb = np.linalg.norm(b)
     return float(np.linalg.norm(a - b) / (nb if nb > 0 else 1.0))
+
+
+def eval_points(u, dofmap, cells, phi):
+    """``out[p] = sum_ijk phi[p,0,i] phi[p,1,j] phi[p,2,k] u[dofmap[cells[p], i n^2 + j n + k]]``:
+    the tensor-product Lagrange interpolant at sample points, i.e. what
+    ``u_n_.eval(x_eval, cell_eval)`` computes in cuda/demo_linear_piston.py:569 (DOLFINx is
+    absent: pinned by polynomial known answers only).  float64 accumulation."""
+    phi = np.asarray(phi, dtype=np.float64)
+    n = phi.shape[2]
+    ue = np.asarray(u, dtype=np.float64)[np.asarray(dofmap)[np.asarray(cells, dtype=np.int64)]]
+    return np.einsum("mi,mj,mk,mijk->m", phi[:, 0], phi[:, 1], phi[:, 2], ue.reshape(-1, n, n, n))

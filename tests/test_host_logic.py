@@ -238,3 +238,48 @@ def test_cell_colouring_is_a_valid_partition(ncells, perturb):
         assert np.array_equal(S.box_cell_colours(p.mesh).reshape(n),
                               whole[o[0]:o[0] + n[0], o[1]:o[1] + n[1], o[2]:o[2] + n[2]])
     assert utils.colour_cells(np.zeros((0, 8), np.int32)).size == 0
+
+
+def test_compute_eval_params_and_interpolation_known_answers():
+    """Point location (the reference's compute_eval_params, cuda/utils.py:117-154) against a
+    brute-force search, and the interpolant against polynomials it must reproduce exactly."""
+    from fenicsx_fus_gpu_b200 import sampling as sp, substrate as S
+    from oracle import oracle as orc
+
+    mesh = S.create_box((5, 4, 3), (1.0, 0.8, 0.6), perturb=0.2, seed=2)
+    rng = np.random.default_rng(0)
+    pts = rng.uniform([-0.1, -0.1, -0.1], [1.1, 0.9, 0.7], (400, 3))
+    xp, cells = sp.compute_eval_params(mesh, pts.T, np.float64)
+    assert xp.shape == (len(cells), 3) and 0 < len(cells) < 400
+    cc = mesh.x_g[mesh.x_dofs]
+    # brute force: pull every point back into every cell
+    nc = mesh.num_cells
+    found = np.full(400, -1)
+    for c in range(nc):
+        X, ok = sp.pull_back(np.broadcast_to(cc[c], (400, 8, 3)), pts)
+        hit = ok & np.all((X >= -1e-9) & (X <= 1 + 1e-9), axis=1) & (found < 0)
+        found[hit] = c
+    assert np.array_equal(np.nonzero(found >= 0)[0], np.nonzero(np.isin(pts, xp).all(axis=1))[0])
+    assert np.array_equal(found[found >= 0], np.asarray(cells))
+    # polynomial of degree <= P in each variable on an affine mesh: reproduced to rounding
+    P = 4
+    tb = S.element_tables(P)
+    box = S.create_box((4, 3, 2), (1.0, 0.8, 0.6))
+    dm = S.tensor_dofmap(box, P)
+    xd = S.dof_coordinates(box, dm, tb)
+    f = lambda x: 1 + x[:, 0] ** 4 * x[:, 1] - x[:, 2] ** 3 + x[:, 0] * x[:, 1] ** 2 * x[:, 2] ** 4  # noqa: E731
+    xp, cells = sp.compute_eval_params(box, pts.T, np.float64)
+    X, phi = sp.reference_basis(box, xp, cells, tb.pts_1d)
+    assert np.abs(phi.sum(axis=2) - 1).max() < 1e-13  # partition of unity
+    assert np.abs(orc.eval_points(f(xd), dm, cells, phi) - f(xp)).max() < 1e-13
+    # nodes are hit exactly: sampling at dof coordinates returns the dof values
+    some = rng.choice(xd.shape[0], 50, replace=False)
+    xp2, c2 = sp.compute_eval_params(box, xd[some].T, np.float64)
+    assert len(c2) == 50
+    _, phi2 = sp.reference_basis(box, xp2, c2, tb.pts_1d)
+    u = rng.standard_normal(xd.shape[0])
+    assert np.abs(orc.eval_points(u, dm, c2, phi2) - u[some]).max() < 1e-12
+    # nothing to find / nothing to search
+    e, c = sp.compute_eval_params(box, np.array([[5.0], [5.0], [5.0]]), np.float32)
+    assert e.shape == (0, 3) and e.dtype == np.float32 and c == []
+    assert sp.compute_eval_params(box, np.zeros((3, 0)), np.float64)[1] == []
