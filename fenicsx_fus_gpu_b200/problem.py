@@ -109,12 +109,18 @@ def box_setup(P, ncells, lengths, dtype=np.float64, rank=0, world=1, comm=None, 
 def facet_group(su: Setup, local_facets, predicate=None):
     """``(bfacet_dofmap (device int32), detJ_f (device), boundary_data (host))`` for the
     exterior facets on the given reference faces (0: z=0, 1: y=0, 2: x=0, 3: x=L, 4: y=L, 5: z=L),
-    optionally filtered by ``predicate(centroids)`` - cuda/demo_linear_box.py:256-333."""
+    optionally filtered by ``predicate(centroids)`` - cuda/demo_linear_box.py:256-333.
+    ``local_facets`` may instead be the ``boundary_data`` array (nf, 2) of
+    ``utils.facet_integration_domain`` (meshes that come from DOLFINx)."""
     import torch
 
     tdt = torch.float64 if su.dtype == np.float64 else torch.float32
-    bds = [S.boundary_facets(su.mesh, f, predicate) for f in local_facets]
-    bd = np.concatenate(bds) if bds else np.zeros((0, 2), np.int32)
+    if isinstance(local_facets, np.ndarray) and local_facets.ndim == 2:
+        # rows (cell, local facet) straight from utils.facet_integration_domain (DOLFINx meshes)
+        bd = np.ascontiguousarray(local_facets, dtype=np.int32)
+    else:
+        bds = [S.boundary_facets(su.mesh, f, predicate) for f in local_facets]
+        bd = np.concatenate(bds) if bds else np.zeros((0, 2), np.int32)
     n2 = su.tables.n**2
     dJ = torch.empty((bd.shape[0], n2), dtype=tdt, device="cuda")
     if bd.shape[0]:

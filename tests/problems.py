@@ -83,3 +83,62 @@ def cfl_dt(P, h, c0, f0, cfl=0.65):
     dt = cfl * h / (c0 * P**2)
     period = 1.0 / f0
     return period / (int(period / dt) + 1)
+
+
+def fake_dolfinx(mesh, dofmap, perm, index_map=None):
+    """Stand-ins for a DOLFINx mesh and function space exposing exactly the attributes the
+    reference demos (and dolfinx_bridge.setup_from_dolfinx / utils.facet_integration_domain)
+    read: mesh.topology.{dim, index_map(d).size_local, connectivity(a, b)},
+    mesh.geometry.{dofmap, x}, V.dofmap.{list, index_map}.  ``V.dofmap.list[:, perm]`` is the
+    tensor-product ``dofmap``.  Returns ``(mesh_like, V_like, facet_id(cell, local_facet))``."""
+    Nx, Ny, Nz = mesh.ncells
+    ncell = Nx * Ny * Nz
+    key_of, f2c = {}, {}
+    c2f = np.zeros((ncell, 6), np.int32)
+    for cx in range(Nx):
+        for cy in range(Ny):
+            for cz in range(Nz):
+                c = (cx * Ny + cy) * Nz + cz
+                for lf in range(6):
+                    axis, side = S._FACE_AXIS[lf]
+                    pos = [cx, cy, cz]
+                    pos[axis] += side
+                    fid = key_of.setdefault((axis, tuple(pos)), len(key_of))
+                    c2f[c, lf] = fid
+                    f2c.setdefault(fid, []).append(c)
+
+    class _Sized:
+        def __init__(self, n):
+            self.size_local = n
+
+    class Topo:
+        dim = 3
+
+        def index_map(self, d):
+            return _Sized(ncell if d == 3 else len(f2c))
+
+        def connectivity(self, a, b):
+            if (a, b) == (3, 2):
+                return S.AdjacencyList(c2f.ravel(), np.arange(0, 6 * ncell + 1, 6))
+            offs = np.cumsum([0] + [len(f2c[f]) for f in range(len(f2c))])
+            return S.AdjacencyList(np.concatenate([f2c[f] for f in range(len(f2c))]), offs)
+
+    class Geo:
+        pass
+
+    class M:
+        topology = Topo()
+        geometry = Geo()
+
+    M.geometry.dofmap, M.geometry.x = mesh.x_dofs, mesh.x_g
+
+    class DM:
+        pass
+
+    class V:
+        dofmap = DM()
+
+    nd = int(dofmap.max()) + 1
+    V.dofmap.list = np.ascontiguousarray(dofmap[:, np.argsort(perm)])
+    V.dofmap.index_map = index_map if index_map is not None else S.serial_index_map(nd)
+    return M(), V(), lambda c, lf: c2f[c, lf]
