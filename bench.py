@@ -146,20 +146,24 @@ def build_problem(rank, world, n_per_gpu, dtype, halo_kind, workload="linear_box
         print(f"[bench] peer-memory halo unavailable ({e!r}); using the NCCL halo", file=sys.stderr, flush=True)
         used = "nccl"
         su = problem.box_setup(deg, ncells, lengths, dtype, rank, world, grid=grid, halo_kind="nccl")
-    if workload == "linear_box":
-        solver = problem.linear_solver(su, source_facets=[2], absorbing_facets=[3], rho=W["rho"], c0=W["c0"],
-                                       f0=W["f0"], p0=P0)
-    elif workload == "linear_piston":
-        piston = problem.disc(0, 1, (0.5 * lengths[0], 0.5 * lengths[1]), 0.01)
-        solver = problem.linear_solver(
-            su, source_facets=[0], absorbing_facets=[0, 1, 2, 3, 4, 5], rho=W["rho"], c0=W["c0"], f0=W["f0"], p0=P0,
-            source_predicate=piston, absorbing_predicate=lambda cen: ~(piston(cen) & (cen[:, 2] < 0.5 * h)))
-    else:
+
+    def make_solver(geometry="stream"):
+        if workload == "linear_box":
+            return problem.linear_solver(su, source_facets=[2], absorbing_facets=[3], rho=W["rho"], c0=W["c0"],
+                                         f0=W["f0"], p0=P0, geometry=geometry)
+        if workload == "linear_piston":
+            piston = problem.disc(0, 1, (0.5 * lengths[0], 0.5 * lengths[1]), 0.01)
+            return problem.linear_solver(
+                su, source_facets=[0], absorbing_facets=[0, 1, 2, 3, 4, 5], rho=W["rho"], c0=W["c0"], f0=W["f0"],
+                p0=P0, source_predicate=piston, geometry=geometry,
+                absorbing_predicate=lambda cen: ~(piston(cen) & (cen[:, 2] < 0.5 * h)))
         centre = (0.5 * lengths[1], 0.5 * lengths[2])
-        solver = problem.westervelt_solver(
+        return problem.westervelt_solver(
             su, source_facets=[2], absorbing_facets=[0, 1, 2, 3, 4, 5], rho=W["rho"], c0=W["c0"], f0=W["f0"],
-            beta=3.5, alpha_dB=0.2, source_predicate=problem.disc(1, 2, centre, 0.3 * lengths[1]))
-    info = dict(ncells_local=su.mesh.num_cells, ndofs_local=su.ndofs, nlocal=su.nlocal, global_cells=ncells,
+            beta=3.5, alpha_dB=0.2, source_predicate=problem.disc(1, 2, centre, 0.3 * lengths[1]), geometry=geometry)
+
+    solver = make_solver()
+    info = dict(make_solver=make_solver, ncells_local=su.mesh.num_cells, ndofs_local=su.ndofs, nlocal=su.nlocal, global_cells=ncells,
                 global_dofs=su.global_dofs, grid=grid, h=h, detJ=su.dev["detJ"], tb=su.tables,
                 dofmap=su.dev["dofmap"], halo=used, degree=deg,
                 dt=problem.cfl_time_step(deg, h, W["c0"], W["f0"], W["cfl"]))
@@ -294,6 +298,7 @@ def main():
                     help="which reference demo to time (default: the headline demo_linear_box)")
     ap.add_argument("--degree", type=int, default=0, help="override the workload's polynomial degree (2..7)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-affine", action="store_true", help="skip the extra affine-geometry measurement")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU halo: fused put/get kernels over NVLink peer memory, or NCCL send/recv")
     ap.add_argument("--no-graph", action="store_true", help="launch the steps eagerly instead of replaying a CUDA graph")
@@ -535,6 +540,54 @@ def main():
     stage_bytes = solver.stage_bytes()
     stage_t = elapsed / (4 * a.steps)
 
+    # ---- the operator through the C ABI with HOST buffers (fus_stiffness_host_*): x from pinned
+    #      host memory, y back to pinned host memory, both copies inside the call ----
+    op_host = None
+    if not W["nonlinear"]:
+        xh = torch.randn(nd, dtype=solver.T).pin_memory()
+        yh = torch.zeros(nd, dtype=solver.T).pin_memory()
+        fh = _lib.fn("fus_stiffness_host", dtype)
+        st = torch.cuda.current_stream().cuda_stream
+
+        def host_call():
+            rc = fh(xh.data_ptr(), yh.data_ptr(), nd, x.data_ptr(), y.data_ptr(), solver.cell_coeff2.data_ptr(),
+                    solver.G.data_ptr(), solver.dofmap.data_ptr(), D.data_ptr(), nc, deg, 0, st)
+            assert rc == 0
+        host_call()
+        barrier()
+        t0h = time.perf_counter()
+        nh = 5
+        for _ in range(nh):
+            host_call()  # synchronous on return
+        th = maxr((time.perf_counter() - t0h) / nh)
+        op_host = {"what": "fus_stiffness_host: y_host += K x_host (H2D x, y; kernel; D2H y) per call",
+                   "value": gdofs_global / th / 1e9, "unit": "GDoF/s", "ms_per_call": th * 1e3,
+                   "h2d_bytes_per_call": 2 * nd * s, "d2h_bytes_per_call": nd * s}
+        del xh, yh
+
+    # ---- the same steps with geometry="auto" (extra, not the headline): cells with a constant
+    #      Jacobian keep 6 geometric factors instead of 6 n^3 (results equal to rounding) ----
+    affine = None
+    if not a.no_affine and (world == 1 or info["halo"] == "nccl"):  # (the peer-memory arena holds one solver's vectors)
+        del x, y
+        sol2 = info["make_solver"]("auto")
+        sol2.use_graph = not a.no_graph
+        sol2.init()
+        sol2.rk4(0.0, dt, warmup)
+        barrier()
+        e0.record()
+        sol2.rk4(sol2.t, dt, a.steps)
+        e1.record()
+        barrier()
+        el2 = maxr(e0.elapsed_time(e1) * 1e-3)
+        affine = {"value": gdofs_global * 4 * a.steps / el2 / 1e9, "unit": "GDoF/s", "ms_per_step": el2 / a.steps * 1e3,
+                  "steps_per_s": a.steps / el2, "affine_cells_per_gpu": sol2.naff, "cells_per_gpu": sol2.ncells,
+                  "algorithmic_bytes_per_stage": sol2.stage_bytes(),
+                  "note": "solver(geometry='auto'): G = wq x Gc on cells with a constant Jacobian (all cells of "
+                          "this box); not the headline because unstructured meshes stream G"}
+        if world > 1:
+            sol2._graph = None
+
     line = {
         "metric": "fused RK4 stage throughput (global dofs x stages / s)", "value": value, "unit": "GDoF/s",
         "workload": a.workload, "n_gpus": world, "steps": a.steps, "warmup": warmup, "ms_per_step": elapsed / a.steps * 1e3,
@@ -549,6 +602,8 @@ def main():
         "stage_roofline": {"bound": "hbm", "achieved": stage_bytes / stage_t / 1e9, "peak": peak, "unit": "GB/s",
                            "frac": stage_bytes / stage_t / 1e9 / peak,
                            "algorithmic_bytes_per_stage": stage_bytes, "stage_ms": stage_t * 1e3},
+        "e2e_operator_host_buffers": op_host,
+        "affine_geometry": affine,
         "operators": {("westervelt_stage_kernel_gdofs" if W["nonlinear"] else "stiffness_gdofs"): info["ndofs_local"] / t_stiff / 1e9, "mass_gdofs": info["ndofs_local"] / t_mass / 1e9,
                       "per_gpu_dofs": info["ndofs_local"]},
     }
