@@ -31,6 +31,9 @@ def _sigs():
         "fus_stiffness_westervelt": [P, P, P, P, P, P, P, P, P, P, P, P, L, I, I, P],
         "fus_stiffness_affine": [P, P, P, P, P, P, P, L, I, I, P],
         "fus_stiffness_westervelt_affine": [P, P, P, P, P, P, P, P, P, P, P, P, P, L, I, I, P],
+        "fus_set_rect_tables": [I, P, P, P],
+        "fus_stiffness_rect": [P, P, P, P, P, P, L, I, I, P],
+        "fus_stiffness_westervelt_rect": [P, P, P, P, P, P, P, P, P, P, P, P, L, I, I, P],
         "fus_compress_geometry": [P, P, P, P, P, P, L, I, T, P],
         "fus_mass": [P, P, P, P, P, L, I, P],
         "fus_axpy": [T, P, P, L, P],

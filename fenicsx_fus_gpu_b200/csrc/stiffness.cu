@@ -75,9 +75,9 @@ int stiffness_entry(const T* xa, const T* ca, const T* xb, const T* cb, T* y, co
   if (mode == 2) {
     if (flags & FUS_NO_ATOMICS)
       return fus_set_error(FUS_ERR_BAD_ARGUMENT, "stiffness_westervelt: FUS_NO_ATOMICS not supported");
-    return launch<T, 2, false>(a, P, flags, st);
+    return launch<T, 2, 0>(a, P, flags, st);
   }
-  return mode == 1 ? launch<T, 1, false>(a, P, flags, st) : launch<T, 0, false>(a, P, flags, st);
+  return mode == 1 ? launch<T, 1, 0>(a, P, flags, st) : launch<T, 0, 0>(a, P, flags, st);
 }
 
 }  // namespace

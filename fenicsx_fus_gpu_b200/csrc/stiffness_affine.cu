@@ -15,10 +15,26 @@
 namespace {
 
 template <typename T>
+int set_rect_tables(int P, const T* k1, const T* w1, cudaStream_t stream) {
+  if (P < 2 || P > 7) return fus_set_error(FUS_ERR_BAD_DEGREE, "set_rect_tables: degree must be 2..7");
+  if (k1 == nullptr || w1 == nullptr) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "set_rect_tables: null table");
+  const int n = P + 1;
+  if constexpr (sizeof(T) == 8) {
+    FUS_CUDA(cudaMemcpyToSymbolAsync(c_K64, k1, sizeof(T) * n * n, sizeof(T) * 64 * (P - 2), cudaMemcpyDefault, stream));
+    FUS_CUDA(cudaMemcpyToSymbolAsync(c_W64, w1, sizeof(T) * n, sizeof(T) * 8 * (P - 2), cudaMemcpyDefault, stream));
+  } else {
+    FUS_CUDA(cudaMemcpyToSymbolAsync(c_K32, k1, sizeof(T) * n * n, sizeof(T) * 64 * (P - 2), cudaMemcpyDefault, stream));
+    FUS_CUDA(cudaMemcpyToSymbolAsync(c_W32, w1, sizeof(T) * n, sizeof(T) * 8 * (P - 2), cudaMemcpyDefault, stream));
+  }
+  return 0;
+}
+
+// geo: 1 = affine (Gc x wq), 2 = rectilinear (diagonal Gc, tensor-product weights; wq unused)
+template <typename T>
 int affine_entry(const T* xa, const T* ca, const T* xb, const T* cb, T* y, const T* Gc,
                  const T* wq, const int32_t* dofmap, const T* dphi, int64_t ncells, int P,
                  int flags, void* stream, int mode, const T* detJc = nullptr,
-                 const T* cm = nullptr, const T* cy = nullptr, T* m = nullptr) {
+                 const T* cm = nullptr, const T* cy = nullptr, T* m = nullptr, int geo = 1) {
   if (ncells < 0) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "stiffness_affine: ncells < 0");
   if (P < 2 || P > 7) return fus_set_error(FUS_ERR_BAD_DEGREE, "stiffness_affine: degree must be 2..7");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -27,7 +43,7 @@ int affine_entry(const T* xa, const T* ca, const T* xb, const T* cb, T* y, const
     if (rc) return rc;
   }
   if (ncells == 0) return 0;
-  if (Gc == nullptr || wq == nullptr)
+  if (Gc == nullptr || (geo == 1 && wq == nullptr))
     return fus_set_error(FUS_ERR_BAD_ARGUMENT, "stiffness_affine: null Gc / wq");
   StiffArgs<T> a;
   a.xa = xa;
@@ -50,9 +66,9 @@ int affine_entry(const T* xa, const T* ca, const T* xb, const T* cb, T* y, const
     if (flags & FUS_NO_ATOMICS)
       return fus_set_error(FUS_ERR_BAD_ARGUMENT, "stiffness_westervelt_affine: FUS_NO_ATOMICS not supported");
     if (detJc == nullptr) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "stiffness_westervelt_affine: null detJc");
-    return launch<T, 2, true>(a, P, flags, st);
+    return geo == 2 ? launch<T, 2, 2>(a, P, flags, st) : launch<T, 2, 1>(a, P, flags, st);
   }
-  return launch<T, 0, true>(a, P, flags, st);
+  return geo == 2 ? launch<T, 0, 2>(a, P, flags, st) : launch<T, 0, 1>(a, P, flags, st);
 }
 
 // one CTA per cell: mean of the weight-normalised records and their largest deviation from it
@@ -166,6 +182,41 @@ int fus_stiffness_westervelt_affine_f32(const float* un, const float* c3, const 
                                         int64_t ncells, int P, int flags, void* stream) {
   return affine_entry<float>(un, c3, vn, c4, b, Gc, wq, dofmap, dphi, ncells, P, flags, stream, 2,
                              detJc, c2, c5, m);
+}
+
+int fus_set_rect_tables_f64(int P, const double* k1, const double* w1, void* stream) {
+  return set_rect_tables<double>(P, k1, w1, static_cast<cudaStream_t>(stream));
+}
+int fus_set_rect_tables_f32(int P, const float* k1, const float* w1, void* stream) {
+  return set_rect_tables<float>(P, k1, w1, static_cast<cudaStream_t>(stream));
+}
+int fus_stiffness_rect_f64(const double* x, const double* coeff, double* y, const double* Gc,
+                           const int32_t* dofmap, const double* dphi, int64_t ncells, int P,
+                           int flags, void* stream) {
+  return affine_entry<double>(x, coeff, nullptr, nullptr, y, Gc, nullptr, dofmap, dphi, ncells, P,
+                              flags, stream, 0, nullptr, nullptr, nullptr, nullptr, 2);
+}
+int fus_stiffness_rect_f32(const float* x, const float* coeff, float* y, const float* Gc,
+                           const int32_t* dofmap, const float* dphi, int64_t ncells, int P, int flags,
+                           void* stream) {
+  return affine_entry<float>(x, coeff, nullptr, nullptr, y, Gc, nullptr, dofmap, dphi, ncells, P, flags,
+                             stream, 0, nullptr, nullptr, nullptr, nullptr, 2);
+}
+int fus_stiffness_westervelt_rect_f64(const double* un, const double* c3, const double* vn,
+                                      const double* c4, const double* c2, const double* c5,
+                                      double* m, double* b, const double* Gc, const double* detJc,
+                                      const int32_t* dofmap, const double* dphi, int64_t ncells,
+                                      int P, int flags, void* stream) {
+  return affine_entry<double>(un, c3, vn, c4, b, Gc, nullptr, dofmap, dphi, ncells, P, flags, stream,
+                              2, detJc, c2, c5, m, 2);
+}
+int fus_stiffness_westervelt_rect_f32(const float* un, const float* c3, const float* vn,
+                                      const float* c4, const float* c2, const float* c5, float* m,
+                                      float* b, const float* Gc, const float* detJc,
+                                      const int32_t* dofmap, const float* dphi, int64_t ncells, int P,
+                                      int flags, void* stream) {
+  return affine_entry<float>(un, c3, vn, c4, b, Gc, nullptr, dofmap, dphi, ncells, P, flags, stream, 2,
+                             detJc, c2, c5, m, 2);
 }
 
 int fus_compress_geometry_f64(const double* G, const double* detJ, const double* wq, double* Gc,

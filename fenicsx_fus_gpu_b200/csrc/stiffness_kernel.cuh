@@ -9,6 +9,11 @@ namespace {
 
 __constant__ double c_D64[6][64];
 __constant__ float c_D32[6][64];
+// rectilinear cells (GEO == 2): 1-D stiffness matrix K1 = D^T diag(w1) D and the 1-D weights
+__constant__ double c_K64[6][64];
+__constant__ float c_K32[6][64];
+__constant__ double c_W64[6][8];
+__constant__ float c_W32[6][8];
 
 template <typename T, int P>
 struct DTable;
@@ -19,6 +24,18 @@ struct DTable<double, P> {
 template <int P>
 struct DTable<float, P> {
   static __device__ __forceinline__ float at(int i) { return c_D32[P - 2][i]; }
+};
+template <typename T, int P>
+struct KTable;
+template <int P>
+struct KTable<double, P> {
+  static __device__ __forceinline__ double at(int i) { return c_K64[P - 2][i]; }
+  static __device__ __forceinline__ double w(int i) { return c_W64[P - 2][i]; }
+};
+template <int P>
+struct KTable<float, P> {
+  static __device__ __forceinline__ float at(int i) { return c_K32[P - 2][i]; }
+  static __device__ __forceinline__ float w(int i) { return c_W32[P - 2][i]; }
 };
 
 // cells per CTA batch / threads per CTA / min CTAs per SM, per (n, sizeof T)
@@ -119,12 +136,21 @@ __device__ __forceinline__ G6<float> load_g6(const float* p) {
 // MODE 0: y += K(ca; xa).  MODE 1: y += K(ca; xa) + K(cb; xb) with one read of G.
 // MODE 2: MODE 1 plus the Westervelt cell-mass pair on the same gathered pencils:
 //         m += M(cm; xa),  y += M(cy; xb^2)   (cuda/demo_nonlinear_bowl.py:609-612, 626-628)
-// AFF: every cell of the launch is affine (constant Jacobian), so its 6*n^3 geometric factors
-// are wq[q] * Gc[cell, 0..5]: nothing is streamed but the dofmap, the shared-memory ring and
-// the TMA copies disappear, and the n quadrature weights a thread needs live in registers.
-template <typename T, int n, int MODE, bool ATOMIC, bool AFF>
+// GEO 0: G streamed through the TMA ring.
+// GEO 1 (affine): every cell of the launch has a constant Jacobian, so its 6*n^3 geometric
+//   factors are wq[q] * Gc[cell, 0..5]: nothing is streamed but the dofmap, the shared-memory
+//   ring and the TMA copies disappear, and the n quadrature weights a thread needs live in
+//   registers.
+// GEO 2 (rectilinear): affine AND Gc diagonal (axis-aligned box cells) with tensor-product
+//   weights: the three directions decouple, y = cc * sum_d g_dd (w x w) (x) K1_d u with the
+//   constant 1-D stiffness matrix K1 = D^T diag(w1) D - one n x n product per pencil and
+//   direction, the y / z pencils are transformed in place (8 tile passes instead of 16, two
+//   barriers instead of five).
+template <typename T, int n, int MODE, bool ATOMIC, int GEO>
 __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
     stiffness_kernel(const StiffArgs<T> a) {
+  constexpr bool AFF = GEO >= 1;
+  constexpr bool RECT = GEO == 2;
   constexpr bool DUAL = MODE >= 1;
   constexpr bool WEST = MODE == 2;
   using L = Layout<T, n>;
@@ -169,7 +195,11 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
   }
   T wreg[AFF ? n : 1];  // affine mode: this thread's quadrature weights w[i, j, k], i = 0..n-1
   (void)wreg;
-  if constexpr (AFF) {
+  if constexpr (RECT) {
+    using KT = KTable<T, n - 1>;
+#pragma unroll
+    for (int i = 0; i < n; ++i) wreg[i] = KT::w(i) * (KT::w(ra) * KT::w(rb));
+  } else if constexpr (AFF) {
 #pragma unroll
     for (int i = 0; i < n; ++i) wreg[i] = lane_ok ? __ldg(a.wq + i * N2 + t2) : T(0);
   }
@@ -332,14 +362,59 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
         uy1[i * L::SPY] = xv[i];
         uz1[i * L::SPZ] = xv[i];
       }
+      if constexpr (!RECT) {
 #pragma unroll
-      for (int i = 0; i < n; ++i) {
-        T acc = T(0);
+        for (int i = 0; i < n; ++i) {
+          T acc = T(0);
 #pragma unroll
-        for (int l = 0; l < n; ++l) acc += D::at(i * n + l) * xv[l];
-        gx[i] = acc;
+          for (int l = 0; l < n; ++l) acc += D::at(i * n + l) * xv[l];
+          gx[i] = acc;
+        }
       }
     }
+    T ry[n];
+    if constexpr (RECT) {
+      using KT = KTable<T, n - 1>;
+      const T wab = KT::w(ra) * KT::w(rb);  // the same product in all three ownerships
+      if (active) {
+        const T sx = cc * gc.g0 * wab;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+          T acc = T(0);
+#pragma unroll
+          for (int l = 0; l < n; ++l) acc += KT::at(i * n + l) * xv[l];
+          if constexpr (WEST) {
+            ry[i] = bex[i] + sx * acc;
+          } else {
+            ry[i] = sx * acc;
+          }
+        }
+      }
+      __syncthreads();
+      if (active) {  // y pencils (i,k) = (ra,rb) and z pencils (i,j) = (rb,ra), in place
+        const T sy = cc * gc.g3 * wab, sz = cc * gc.g5 * wab;
+        T u[n];
+#pragma unroll
+        for (int l = 0; l < n; ++l) u[l] = uy2[l * n];
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+          T acc = T(0);
+#pragma unroll
+          for (int l = 0; l < n; ++l) acc += KT::at(j * n + l) * u[l];
+          uy2[j * n] = sy * acc;
+        }
+#pragma unroll
+        for (int l = 0; l < n; ++l) u[l] = uz3[l];
+#pragma unroll
+        for (int k = 0; k < n; ++k) {
+          T acc = T(0);
+#pragma unroll
+          for (int l = 0; l < n; ++l) acc += KT::at(k * n + l) * u[l];
+          uz3[k] = sz * acc;
+        }
+      }
+      __syncthreads();
+    } else {
     __syncthreads();
 
     // ---- y pencils (i,k) = (ra,rb); z pencils (i,j) = (rb,ra) ---------------
@@ -376,7 +451,6 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
     __syncthreads();
 
     // ---- geometric transform at (i, j, k), (j,k) = (ra,rb); x-direction D^T --
-    T ry[n];
     if (active) {
       const T* Gc = Gs + cs * (L::GC / L::S) + t2 * 6;
 #pragma unroll
@@ -434,6 +508,7 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
       }
     }
     __syncthreads();
+    }  // !RECT
 
     // ---- sum the three directions and scatter-add the x pencil --------------
     if (active) {
@@ -459,11 +534,11 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
   }
 }
 
-template <typename T, int n, int MODE, bool ATOMIC, bool AFF>
+template <typename T, int n, int MODE, bool ATOMIC, int GEO>
 int launch_cfg(const StiffArgs<T>& a, cudaStream_t stream) {
   using L = Layout<T, n>;
-  constexpr int SMEM = AFF ? L::SMEM_AFF : L::SMEM;
-  auto kern = stiffness_kernel<T, n, MODE, ATOMIC, AFF>;
+  constexpr int SMEM = GEO ? L::SMEM_AFF : L::SMEM;
+  auto kern = stiffness_kernel<T, n, MODE, ATOMIC, GEO>;
   static int blocks_per_sm = 0;  // per instantiation
   if (blocks_per_sm == 0) {
     FUS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -479,13 +554,13 @@ int launch_cfg(const StiffArgs<T>& a, cudaStream_t stream) {
   return 0;
 }
 
-template <typename T, int MODE, bool AFF>
+template <typename T, int MODE, int GEO>
 int launch(const StiffArgs<T>& a, int P, int flags, cudaStream_t stream) {
   const bool atomic = !(flags & FUS_NO_ATOMICS);
 #define FUS_CASE(N)                                                       \
   case N - 1:                                                             \
-    return atomic ? launch_cfg<T, N, MODE, true, AFF>(a, stream)          \
-                  : launch_cfg<T, N, MODE == 2 ? 1 : MODE, false, AFF>(a, stream);
+    return atomic ? launch_cfg<T, N, MODE, true, GEO>(a, stream)          \
+                  : launch_cfg<T, N, MODE == 2 ? 1 : MODE, false, GEO>(a, stream);
   switch (P) {
     FUS_CASE(3)
     FUS_CASE(4)

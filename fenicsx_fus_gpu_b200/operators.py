@@ -161,6 +161,57 @@ class _StiffnessAffine(_Kernel):
                                             self.P, 0, current_stream()), "fus_stiffness_affine")
 
 
+def rect_tables(dphi_1D, weights, float_type):
+    """``(K1, w1)`` for the rectilinear kernels from the 1-D derivative table ``dphi_1D[q, i]``
+    and the tensor quadrature weights (n^3,): ``w1`` with ``weights = w1 x w1 x w1`` and
+    ``K1 = D^T diag(w1) D``.  Raises when the weights are not a tensor product."""
+    D = np.asarray(dphi_1D, dtype=np.float64)
+    n = D.shape[0]
+    wq = np.asarray(weights, dtype=np.float64).reshape(n, n, n)
+    w1 = wq.sum(axis=(1, 2)) / wq.sum() ** (2.0 / 3.0)
+    rtol = 1e-12 if np.dtype(float_type) == np.float64 else 1e-5
+    if not np.allclose(w1[:, None, None] * w1[None, :, None] * w1[None, None, :], wq, rtol=rtol, atol=0.0):
+        raise ValueError("rect_tables: the quadrature weights are not a tensor product")
+    k1 = (D.T * w1[None, :]) @ D
+    return np.ascontiguousarray(k1, dtype=float_type), np.ascontiguousarray(w1, dtype=float_type)
+
+
+class _StiffnessRect(_Kernel):
+    """The stiffness action on rectilinear cells (affine with diagonal ``Gc``): three decoupled
+    1-D products with ``K1 = D^T diag(w1) D``.  Same call as ``stiffness_operator_affine``."""
+
+    def __init__(self, P: int, float_type):
+        if not 2 <= int(P) <= 7:
+            raise ValueError(f"stiffness_operator_rect: degree {P} not in 2..7")
+        self.P, self.n, self.float_type = int(P), int(P) + 1, np.dtype(float_type)
+        _lib.sfx(self.float_type)
+
+    def __call__(self, x, entity_constants, y, Gc, weights, entity_dofmap, dphi):
+        T = self.float_type
+        xd, yd, cd, gd = dev(x, T), dev(y, T), dev(entity_constants, T), dev(Gc, T)
+        dm = dev(entity_dofmap, np.int32)
+        nd3 = self.n**3
+        if len(dm.shape) != 2 or dm.shape[1] != nd3:
+            raise _lib.FusError(f"stiffness_operator_rect: dofmap must be (ncells, {nd3}), got {dm.shape}")
+        if gd.size != dm.shape[0] * 6 or cd.size != dm.shape[0]:
+            raise _lib.FusError("stiffness_operator_rect: Gc (ncells, 6), constants (ncells,)")
+        if dm.shape[0] == 0:
+            raise ValueError("stiffness_operator_rect: zero cells (empty launch)")
+        if not isinstance(dphi, np.ndarray) or not isinstance(weights, np.ndarray):
+            raise _lib.FusError("stiffness_operator_rect: dphi and weights are host tables (numpy)")
+        k1, w1 = rect_tables(dphi, weights, T)
+        st = current_stream()
+        check(fn("fus_set_rect_tables", T)(self.P, k1.ctypes.data, w1.ctypes.data, st), "fus_set_rect_tables")
+        check(fn("fus_stiffness_rect", T)(xd.ptr, cd.ptr, yd.ptr, gd.ptr, dm.ptr, None, dm.shape[0], self.P,
+                                          FUS_TABLES_RESIDENT, st), "fus_stiffness_rect")
+
+
+def stiffness_operator_rect(P, float_type):
+    """Stiffness kernel for rectilinear cells (not in the reference):
+    ``k[grid, block](x, constants, y, Gc, weights, dofmap, dphi_1D)`` with host tables."""
+    return _StiffnessRect(P, float_type)
+
+
 def stiffness_operator_affine(P, float_type):
     """Stiffness kernel for affine cells (not in the reference):
     ``k[grid, block](x, constants, y, Gc, weights, dofmap, dphi)``."""

@@ -148,13 +148,33 @@ class _RK4:
             raise ValueError("geometry='auto' needs the quadrature weights (n^3,)")
         self.geometry = geometry
         self._weights = None if weights is None else _dev(weights, self.T)
-        self.naff = 0  # cells [0, naff) are affine (after the set-up permutation)
+        self.nrect = 0  # cells [0, nrect) are rectilinear (affine, diagonal Gc), after the set-up permutation
+        self.naff = 0  # cells [0, naff) are affine: [nrect, naff) go through the general affine kernel
         self.Gc = self.detJc = None
+        self._rect_tables = None
 
     # ---- set-up helpers ------------------------------------------------------
     def _set_tables(self):
         check(fn("fus_set_dphi", self.dtype)(self.P, self._dphi_host.ctypes.data, current_stream()),
               "fus_set_dphi")
+        if self._rect_tables is not None:
+            k1, w1 = self._rect_tables
+            check(fn("fus_set_rect_tables", self.dtype)(self.P, k1.ctypes.data, w1.ctypes.data, current_stream()),
+                  "fus_set_rect_tables")
+
+    def _tensor_weights(self):
+        """1-D weights w1 with weights[i n^2 + j n + k] = w1[i] w1[j] w1[k], or None when the rule
+        is not a tensor product (then no cell takes the rectilinear path)."""
+        n = self.n
+        wq = self._weights.cpu().numpy().astype(np.float64).reshape(n, n, n)
+        tot = wq.sum()
+        if not tot > 0:
+            return None
+        w1 = wq.sum(axis=(1, 2)) / tot ** (2.0 / 3.0)
+        rtol = 1e-12 if self.dtype == np.float64 else 1e-5
+        if not np.allclose(w1[:, None, None] * w1[None, :, None] * w1[None, None, :], wq, rtol=rtol, atol=0.0):
+            return None
+        return w1
 
     def _mass(self, x, coeff, y, detJ, dofmap):
         if dofmap.shape[0]:
@@ -192,23 +212,36 @@ class _RK4:
         from . import precompute as pre
 
         affine, Gc, detJc = pre.compress_geometry(self.G, detJ, self._weights)
-        na = int(affine.sum().item())
+        # rectilinear = affine with a diagonal Gc (off-diagonal factors at rounding-noise level)
+        w1 = self._tensor_weights()
+        tol = 2048.0 * float(np.finfo(self.dtype).eps)
+        diag = Gc[:, [0, 3, 5]].abs().amax(dim=1)
+        off = Gc[:, [1, 2, 4]].abs().amax(dim=1)
+        rect = (affine > 0) & (off <= tol * diag) if w1 is not None else torch.zeros_like(affine, dtype=torch.bool)
+        kind = torch.where(rect, 0, torch.where(affine > 0, 1, 2)).to(torch.int32)  # 0 rect, 1 affine, 2 streamed
+        na = int((kind < 2).sum().item())
+        nr = int((kind == 0).sum().item())
         nc = self.ncells
-        self.naff = na
+        self.naff, self.nrect = na, nr
+        if nr:
+            D = self._dphi_host.astype(np.float64)
+            k1 = np.ascontiguousarray((D.T * w1[None, :]) @ D, dtype=self.dtype)  # K1 = D^T diag(w1) D
+            self._rect_tables = (k1, np.ascontiguousarray(w1, dtype=self.dtype))
         if na == 0:
             return
-        if na < nc:
-            perm = torch.argsort(1 - affine, stable=True)  # affine cells first, original order kept
+        if not (nr in (0, nc) and na in (0, nc)):
+            perm = torch.argsort(kind, stable=True)  # rectilinear, affine, streamed; original order kept inside
             self.cell_perm = perm
             self.dofmap = self.dofmap[perm].contiguous()
             for name in cell_arrays:
                 setattr(self, name, getattr(self, name)[perm].contiguous())
             Gc, detJc = Gc[perm], detJc[perm]
             rest = perm[na:]
-            self.G = self.G[rest].contiguous()
-            if detJ is not None:
-                self.detJ = detJ[rest].contiguous()
-        else:
+            if na < nc:
+                self.G = self.G[rest].contiguous()
+                if detJ is not None:
+                    self.detJ = detJ[rest].contiguous()
+        if na == nc:
             self.G = None  # nothing left to stream (the caller's tensor is not touched)
             if detJ is not None:
                 self.detJ = None
@@ -442,12 +475,16 @@ class LinearSpectral3D(_RK4):
         self._setup_geometry(None, ["cell_coeff2"])
 
     def _stiffness(self):
-        na, nc, st = self.naff, self.ncells, current_stream()
-        if na:  # affine cells: 6 factors per cell, nothing streamed but the dofmap
-            check(fn("fus_stiffness_affine", self.dtype)(
+        nr, na, nc, st = self.nrect, self.naff, self.ncells, current_stream()
+        if nr:  # rectilinear cells: three decoupled 1-D stiffness products
+            check(fn("fus_stiffness_rect", self.dtype)(
                 self.un.data_ptr(), self.cell_coeff2.data_ptr(), self.b.data_ptr(), self.Gc.data_ptr(),
-                self._weights.data_ptr(), self.dofmap.data_ptr(), None, na, self.P, FUS_TABLES_RESIDENT, st),
-                "fus_stiffness_affine")
+                self.dofmap.data_ptr(), None, nr, self.P, FUS_TABLES_RESIDENT, st), "fus_stiffness_rect")
+        if na > nr:  # affine cells: 6 factors per cell, nothing streamed but the dofmap
+            check(fn("fus_stiffness_affine", self.dtype)(
+                self.un.data_ptr(), self.cell_coeff2[nr:].data_ptr(), self.b.data_ptr(), self.Gc[nr:].data_ptr(),
+                self._weights.data_ptr(), self.dofmap[nr:].data_ptr(), None, na - nr, self.P,
+                FUS_TABLES_RESIDENT, st), "fus_stiffness_affine")
         if na < nc:
             check(fn("fus_stiffness", self.dtype)(
                 self.un.data_ptr(), self.cell_coeff2[na:].data_ptr(), self.b.data_ptr(), self.G.data_ptr(),
@@ -529,13 +566,20 @@ class WesterveltSpectral3D(_RK4):
         self._boundary(stage, g, dg, use_table)
 
     def _stage_kernel(self):
-        na, nc, st = self.naff, self.ncells, current_stream()
-        if na:
-            check(fn("fus_stiffness_westervelt_affine", self.dtype)(
+        nr, na, nc, st = self.nrect, self.naff, self.ncells, current_stream()
+        if nr:
+            check(fn("fus_stiffness_westervelt_rect", self.dtype)(
                 self.un.data_ptr(), self.c3.data_ptr(), self.ku.data_ptr(), self.c4.data_ptr(),
                 self.c2.data_ptr(), self.c5.data_ptr(), self.m.data_ptr(), self.b.data_ptr(),
-                self.Gc.data_ptr(), self.detJc.data_ptr(), self._weights.data_ptr(), self.dofmap.data_ptr(),
-                None, na, self.P, FUS_TABLES_RESIDENT, st), "fus_stiffness_westervelt_affine")
+                self.Gc.data_ptr(), self.detJc.data_ptr(), self.dofmap.data_ptr(), None, nr, self.P,
+                FUS_TABLES_RESIDENT, st), "fus_stiffness_westervelt_rect")
+        if na > nr:
+            check(fn("fus_stiffness_westervelt_affine", self.dtype)(
+                self.un.data_ptr(), self.c3[nr:].data_ptr(), self.ku.data_ptr(), self.c4[nr:].data_ptr(),
+                self.c2[nr:].data_ptr(), self.c5[nr:].data_ptr(), self.m.data_ptr(), self.b.data_ptr(),
+                self.Gc[nr:].data_ptr(), self.detJc[nr:].data_ptr(), self._weights.data_ptr(),
+                self.dofmap[nr:].data_ptr(), None, na - nr, self.P, FUS_TABLES_RESIDENT, st),
+                "fus_stiffness_westervelt_affine")
         if na < nc:
             check(fn("fus_stiffness_westervelt", self.dtype)(
                 self.un.data_ptr(), self.c3[na:].data_ptr(), self.ku.data_ptr(), self.c4[na:].data_ptr(),

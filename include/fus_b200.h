@@ -127,6 +127,34 @@ int fus_stiffness_westervelt_affine_f32(const float* un, const float* c3, const 
                                         const float* wq, const int32_t* dofmap, const float* dphi,
                                         int64_t ncells, int P, int flags, void* stream);
 
+/* Rectilinear cells: affine AND Gc diagonal (axis-aligned box cells: Gc[c,1] = Gc[c,2] =
+ * Gc[c,4] = 0) with tensor-product weights wq[i n^2 + j n + k] = w1[i] w1[j] w1[k].  The three
+ * directions decouple,
+ *   y = coeff * sum_d Gc[c,dd] * (w1 x w1) (x) K1 u,   K1 = D^T diag(w1) D  (n x n, constant),
+ * so each pencil needs one n x n product per direction and no gradient ever changes
+ * ownership: half the shared-memory traffic and FP work of the affine kernels.  Same operator
+ * as fus_stiffness_* on such cells (results agree to rounding).  fus_set_rect_tables uploads
+ * K1 (n*n, row-major) and w1 (n) for degree P (host or device pointers); Gc is (ncells, 6) as
+ * above (entries 0, 3, 5 are read). */
+int fus_set_rect_tables_f64(int P, const double* k1, const double* w1, void* stream);
+int fus_set_rect_tables_f32(int P, const float* k1, const float* w1, void* stream);
+int fus_stiffness_rect_f64(const double* x, const double* coeff, double* y, const double* Gc,
+                           const int32_t* dofmap, const double* dphi, int64_t ncells, int P,
+                           int flags, void* stream);
+int fus_stiffness_rect_f32(const float* x, const float* coeff, float* y, const float* Gc,
+                           const int32_t* dofmap, const float* dphi, int64_t ncells, int P, int flags,
+                           void* stream);
+int fus_stiffness_westervelt_rect_f64(const double* un, const double* c3, const double* vn,
+                                      const double* c4, const double* c2, const double* c5,
+                                      double* m, double* b, const double* Gc, const double* detJc,
+                                      const int32_t* dofmap, const double* dphi, int64_t ncells,
+                                      int P, int flags, void* stream);
+int fus_stiffness_westervelt_rect_f32(const float* un, const float* c3, const float* vn,
+                                      const float* c4, const float* c2, const float* c5, float* m,
+                                      float* b, const float* Gc, const float* detJc,
+                                      const int32_t* dofmap, const float* dphi, int64_t ncells, int P,
+                                      int flags, void* stream);
+
 /* Per cell: Gc[c,:] = mean_q G[c,q,:] / wq[q], detJc[c] = mean_q detJ[c,q] / wq[q] (detJ may be
  * NULL) and affine[c] = 1 when every G[c,q,:] / wq[q] (and detJ[c,q] / wq[q]) lies within
  * tol * max|Gc[c,:]| (tol * |detJc[c]|) of that mean, else 0.  One CTA per cell. */

@@ -31,7 +31,7 @@ def rel_l2(a, b):
     return float(np.linalg.norm(a - b) / np.linalg.norm(b))
 
 
-def sheared_box(ncells, L, dt, jitter_below=None, seed=0):
+def sheared_box(ncells, L, dt, jitter_below=None, seed=0, shear=True):
     """Box of parallelepipeds (every cell affine, all six entries of G non-zero); with
     ``jitter_below`` the vertices with x < jitter_below * L are perturbed, which makes the
     cells touching them non-affine.  Returns (mesh, expected affine mask)."""
@@ -45,7 +45,7 @@ def sheared_box(ncells, L, dt, jitter_below=None, seed=0):
         h = L / max(mesh.ncells)
         moved = x[:, 0] < jitter_below * L
         x[moved] += rng.uniform(-0.15, 0.15, (int(moved.sum()), 3)) * h
-    mesh.x_g = np.ascontiguousarray(x @ SHEAR.T, dtype=dt)
+    mesh.x_g = np.ascontiguousarray(x @ SHEAR.T if shear else x, dtype=dt)
     return mesh, ~moved[mesh.x_dofs].any(axis=1)
 
 
@@ -103,17 +103,58 @@ def test_affine_stiffness_vs_oracle(P, tag):
         K[Nc, (n, n, n)](d(x), d(coeff), y, Gc[:-1], d(tb.wts), d(dofmap), tb.dphi_1D)
 
 
-@pytest.mark.parametrize("P,N,tag,jitter", [(4, 5, "f64", None), (4, 5, "f64", 0.5), (3, 6, "f32", 0.5),
-                                            (5, 3, "f64", 0.4), (2, 7, "f64", 1.1)])
-def test_linear_rk4_auto_geometry_vs_oracle(P, N, tag, jitter):
-    """All-affine, mixed and no-affine-cell meshes through geometry='auto'."""
+@pytest.mark.parametrize("P", range(2, 8))
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+def test_rect_stiffness_vs_oracle(P, tag):
+    """Axis-aligned cells of unequal sizes: the decoupled 1-D-stiffness kernel against the
+    reference algorithm with the full tables."""
+    import problems
+    from fenicsx_fus_gpu_b200 import operators as ops, precompute as pre, substrate as S
+    from oracle import oracle as orc
+
+    dt = np.float64 if tag == "f64" else np.float32
+    tb = S.element_tables(P, "basix", dt)
+    N = (9, 5, 4) if P <= 4 else (4, 3, 3)
+    mesh = S.create_box(N, (1.0, 0.7, 1.9), dtype=np.float64)
+    x = mesh.x_g.copy()  # grade the grid: still axis-aligned, every cell a different box
+    for ax in range(3):
+        x[:, ax] = x[:, ax] + 0.08 * np.sin(2.5 * x[:, ax])
+    mesh.x_g = np.ascontiguousarray(x, dtype=dt)
+    dofmap = S.tensor_dofmap(mesh, P)
+    nd, Nc, n = int(dofmap.max()) + 1, dofmap.shape[0], P + 1
+    G, _ = problems.geometry(mesh, tb, dt)
+    rng = np.random.default_rng(P)
+    xv = rng.standard_normal(nd).astype(dt)
+    coeff = rng.uniform(0.5, 2.0, Nc).astype(dt)
+    y_ref = np.zeros(nd, dt)
+    orc.stiffness_operator(P, xv, coeff, y_ref, G, dofmap, tb.dphi_1D)
+    affine, Gc, _ = pre.compress_geometry(d(G), None, d(tb.wts))
+    assert bool(affine.all())
+    assert float(Gc[:, [1, 2, 4]].abs().max()) <= 1e-5 * float(Gc[:, [0, 3, 5]].abs().max())
+    y = torch.zeros(nd, dtype=d(xv).dtype, device="cuda")
+    K = ops.stiffness_operator_rect(P, dt)
+    K[Nc, (n, n, n)](d(xv), d(coeff), y, Gc, tb.wts, d(dofmap), tb.dphi_1D)
+    assert rel_l2(y.cpu().numpy(), y_ref) < TOL[tag]
+    K[Nc, (n, n, n)](d(xv), d(coeff), y, Gc, tb.wts, d(dofmap), tb.dphi_1D)  # accumulates
+    assert rel_l2(0.5 * y.cpu().numpy(), y_ref) < TOL[tag]
+    with pytest.raises(ValueError):
+        ops.rect_tables(tb.dphi_1D, rng.uniform(1, 2, n**3), dt)  # not a tensor-product rule
+
+
+@pytest.mark.parametrize("P,N,tag,jitter,shear", [(4, 5, "f64", None, True), (4, 5, "f64", 0.5, True),
+                                                  (3, 6, "f32", 0.5, True), (5, 3, "f64", 0.4, True),
+                                                  (2, 7, "f64", 1.1, True), (4, 5, "f64", None, False),
+                                                  (4, 5, "f64", 0.5, False), (6, 3, "f32", 0.4, False)])
+def test_linear_rk4_auto_geometry_vs_oracle(P, N, tag, jitter, shear):
+    """All-affine, mixed and no-affine-cell meshes through geometry='auto'; without the shear
+    the affine cells are rectilinear and take the decoupled kernel."""
     import problems
     import test_gpu_solver as tgs
     from fenicsx_fus_gpu_b200 import substrate as S
 
     dtt = np.float64 if tag == "f64" else np.float32
     L = 0.01
-    mesh, expect = sheared_box(N, L, dtt, jitter_below=jitter, seed=P)
+    mesh, expect = sheared_box(N, L, dtt, jitter_below=jitter, seed=P, shear=shear)
     dofmap = S.tensor_dofmap(mesh, P)
     dd = problems.linear_problem(P, N, L, dtt, mesh=mesh, dofmap=dofmap, ndofs=int(dofmap.max()) + 1)
     dt = problems.cfl_dt(P, 0.8 * L / N, dd.c0, dd.f0)
@@ -122,7 +163,7 @@ def test_linear_rk4_auto_geometry_vs_oracle(P, N, tag, jitter):
     assert np.linalg.norm(u_ref) > 0
     for use_graph in (True, False):
         s = tgs._linear_solver(dd, dtt, geometry="auto", weights=dd.tb.wts, use_graph=use_graph)
-        assert s.naff == int(expect.sum())
+        assert s.naff == int(expect.sum()) and s.nrect == (0 if shear else s.naff)
         s.init()
         s.rk4(0.0, dt, nsteps)
         assert rel_l2(s.u.cpu().numpy(), u_ref) < TOL[tag]
@@ -131,8 +172,10 @@ def test_linear_rk4_auto_geometry_vs_oracle(P, N, tag, jitter):
         tgs._linear_solver(dd, dtt, geometry="auto")  # needs the quadrature weights
 
 
-@pytest.mark.parametrize("P,N,tag,jitter", [(4, 4, "f64", None), (4, 4, "f64", 0.5), (3, 5, "f32", 0.5)])
-def test_westervelt_rk4_auto_geometry_vs_oracle(P, N, tag, jitter):
+@pytest.mark.parametrize("P,N,tag,jitter,shear", [(4, 4, "f64", None, True), (4, 4, "f64", 0.5, True),
+                                                  (3, 5, "f32", 0.5, True), (4, 4, "f64", None, False),
+                                                  (4, 4, "f64", 0.5, False), (5, 3, "f32", None, False)])
+def test_westervelt_rk4_auto_geometry_vs_oracle(P, N, tag, jitter, shear):
     import problems
     from fenicsx_fus_gpu_b200 import substrate as S
     from fenicsx_fus_gpu_b200.solver import WesterveltSpectral3D, westervelt_source
@@ -140,7 +183,7 @@ def test_westervelt_rk4_auto_geometry_vs_oracle(P, N, tag, jitter):
 
     dtt = np.float64 if tag == "f64" else np.float32
     L = 0.006
-    mesh, expect = sheared_box(N, L, dtt, jitter_below=jitter, seed=3)
+    mesh, expect = sheared_box(N, L, dtt, jitter_below=jitter, seed=3, shear=shear)
     dofmap = S.tensor_dofmap(mesh, P)
     q = problems.westervelt_problem(P, N, L, dtt, mesh=mesh, dofmap=dofmap, ndofs=int(dofmap.max()) + 1)
     dt = problems.cfl_dt(P, 0.8 * L / N, q.c0, q.f0, cfl=0.4)
@@ -161,7 +204,7 @@ def test_westervelt_rk4_auto_geometry_vs_oracle(P, N, tag, jitter):
         q.cell_coeff3, q.cell_coeff4, q.cell_coeff5, q.bfacet_dofmap1, q.detJ_f1, q.facet_coeff1_1,
         q.facet_coeff2_1, q.bfacet_dofmap2, q.detJ_f2, q.facet_coeff1_2, q.facet_coeff2_2,
         source=lambda t: westervelt_source(t, q.f0, q.p0, q.c0), geometry="auto", weights=q.tb.wts)
-    assert s.naff == int(expect.sum())
+    assert s.naff == int(expect.sum()) and s.nrect == (0 if shear else s.naff)
     s.init()
     s.rk4(0.0, dt, nsteps)
     assert rel_l2(s.u.cpu().numpy(), u_ref) < TOL[tag]

@@ -104,6 +104,13 @@ def main():
             wq = torch.from_numpy(tb.wts).cuda()
             f = lambda: Ka[Nc, (n, n, n)](x, c, y, Gc, wq, dofmap, D)  # noqa: E731
             bytes_ = Nc * (Nd * 4 + 7 * s) + 2 * s * nd
+        elif op == "rect":
+            # rectilinear cells: three decoupled 1-D stiffness products (fus_stiffness_rect)
+            aff, Gc, _ = pre.compress_geometry(G, None, torch.from_numpy(tb.wts).cuda())
+            assert bool(aff.all()), "mesh has non-affine cells (use --perturb 0)"
+            Kr = ops.stiffness_operator_rect(P, dt)
+            f = lambda: Kr[Nc, (n, n, n)](x, c, y, Gc, tb.wts, dofmap, tb.dphi_1D)  # noqa: E731
+            bytes_ = Nc * (Nd * 4 + 7 * s) + 2 * s * nd
         elif op == "mass":
             f = lambda: ops.mass_operator[1, 128](x, c, y, detJ, dofmap)  # noqa: E731
             bytes_ = Nc * (Nd * (4 + s) + s) + 2 * s * nd
