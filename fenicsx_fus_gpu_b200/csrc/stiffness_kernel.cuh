@@ -282,7 +282,36 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
   (void)djn;
   (void)bex;
 
+  // Rectilinear mode uses the per-cell scalars right at the top of a batch (the other modes
+  // first need them two barriers later), so they ride the register pipeline one batch ahead:
+  // [0..2] Gc diagonal, then coeff | (ca, cb) | (ca, cb, cm, cy, detJc).
+  constexpr int NCS = RECT ? 3 + (DUAL ? (WEST ? 5 : 2) : 1) : 1;
+  T csc[NCS], cscn[NCS];
+  (void)csc;
+  (void)cscn;
+  auto load_cell_scalars = [&](long long b, T* c) {
+    if constexpr (RECT) {
+      const long long cell = b * B + cs;
+      const bool ok = lane_ok && b < nb && cell < a.ncells;
+#pragma unroll
+      for (int q = 0; q < NCS; ++q) c[q] = T(0);
+      if (ok) {
+        c[0] = __ldg(a.Gc + cell * 6);
+        c[1] = __ldg(a.Gc + cell * 6 + 3);
+        c[2] = __ldg(a.Gc + cell * 6 + 5);
+        c[3] = __ldg(a.ca + cell);
+        if constexpr (DUAL) c[4] = __ldg(a.cb + cell);
+        if constexpr (WEST) {
+          c[5] = __ldg(a.cm + cell);
+          c[6] = __ldg(a.cy + cell);
+          c[7] = __ldg(a.detJc + cell);
+        }
+      }
+    }
+  };
+
   // prologue: first batch of this CTA
+  load_cell_scalars(blockIdx.x, csc);
   if constexpr (!AFF) {
     if (tid < 32 && (long long)blockIdx.x < nb && bulk_eligible(blockIdx.x)) issue(blockIdx.x, 0);
   }
@@ -310,7 +339,12 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
     T djc = T(0);
     (void)gc;
     (void)djc;
-    if constexpr (AFF) {
+    if constexpr (RECT) {
+      gc.g0 = csc[0];
+      gc.g3 = csc[1];
+      gc.g5 = csc[2];
+      if constexpr (WEST) djc = csc[7];
+    } else if constexpr (AFF) {
       if (active) {
         const T* p = a.Gc + (cell0 + cs) * 6;
         gc = {__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3), __ldg(p + 4), __ldg(p + 5)};
@@ -331,15 +365,17 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
     load_dofs(bn + stride, dofm);
     load_x(dofn, xvn, xwn);
     if constexpr (WEST && !AFF) load_detj(bn, reinterpret_cast<T(&)[n]>(djn));
+    load_cell_scalars(bn, cscn);
 
     // ---- x pencil (registers) -> tiles; x-direction gradient ----------------
     T gx[n];
     T cc = T(1);
     if (active) {
       if constexpr (DUAL) {
-        const T ca = a.ca[cell0 + cs], cb = a.cb[cell0 + cs];
+        const T ca = RECT ? csc[3] : a.ca[cell0 + cs], cb = RECT ? csc[NCS > 4 ? 4 : 0] : a.cb[cell0 + cs];
         if constexpr (WEST) {
-          const T cm = a.cm[cell0 + cs], cy = a.cy[cell0 + cs];
+          const T cm = RECT ? csc[NCS > 5 ? 5 : 0] : a.cm[cell0 + cs];
+          const T cy = RECT ? csc[NCS > 6 ? 6 : 0] : a.cy[cell0 + cs];
 #pragma unroll
           for (int i = 0; i < n; ++i) {
             T dji;
@@ -355,7 +391,7 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
 #pragma unroll
         for (int i = 0; i < n; ++i) xv[i] = ca * xv[i] + cb * xw[i];
       } else {
-        cc = a.ca[cell0 + cs];
+        cc = RECT ? csc[NCS > 3 ? 3 : 0] : a.ca[cell0 + cs];
       }
 #pragma unroll
       for (int i = 0; i < n; ++i) {
@@ -529,6 +565,10 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
       xv[i] = xvn[i];
       if constexpr (DUAL) xw[i] = xwn[i];
       if constexpr (WEST && !AFF) dj[i] = djn[i];
+    }
+    if constexpr (RECT) {
+#pragma unroll
+      for (int q = 0; q < NCS; ++q) csc[q] = cscn[q];
     }
     __syncthreads();  // tiles and stage s are free again
   }
