@@ -125,7 +125,7 @@ WORKLOADS = {
 }
 
 
-def build_problem(rank, world, n_per_gpu, dtype, halo_kind, workload="linear_box", degree=None):
+def build_problem(rank, world, n_per_gpu, dtype, halo_kind, workload="linear_box", degree=None, geometry="stream"):
     """The demo's preamble through fenicsx_fus_gpu_b200.problem (device geometry,
     block partition, halo).  Returns the solver and an info dict."""
     from fenicsx_fus_gpu_b200 import problem
@@ -162,7 +162,7 @@ def build_problem(rank, world, n_per_gpu, dtype, halo_kind, workload="linear_box
             su, source_facets=[2], absorbing_facets=[0, 1, 2, 3, 4, 5], rho=W["rho"], c0=W["c0"], f0=W["f0"],
             beta=3.5, alpha_dB=0.2, source_predicate=problem.disc(1, 2, centre, 0.3 * lengths[1]), geometry=geometry)
 
-    solver = make_solver()
+    solver = make_solver(geometry)
     info = dict(make_solver=make_solver, ncells_local=su.mesh.num_cells, ndofs_local=su.ndofs, nlocal=su.nlocal, global_cells=ncells,
                 global_dofs=su.global_dofs, grid=grid, h=h, detJ=su.dev["detJ"], tb=su.tables,
                 dofmap=su.dev["dofmap"], halo=used, degree=deg,
@@ -299,6 +299,9 @@ def main():
     ap.add_argument("--degree", type=int, default=0, help="override the workload's polynomial degree (2..7)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-affine", action="store_true", help="skip the extra affine-geometry measurement")
+    ap.add_argument("--geometry", default="stream", choices=["stream", "auto"],
+                    help="stream (default, the reference's data flow: G read in full every stage) or auto "
+                         "(cells with a constant Jacobian keep 6 factors; the JSON line says so in config)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU halo: fused put/get kernels over NVLink peer memory, or NCCL send/recv")
     ap.add_argument("--no-graph", action="store_true", help="launch the steps eagerly instead of replaying a CUDA graph")
@@ -354,7 +357,10 @@ def main():
     dtype = np.float64 if a.dtype == "f64" else np.float32
     s = np.dtype(dtype).itemsize
     log("building the problem")
-    solver, info = build_problem(rank, world, n_per_gpu, dtype, a.halo, a.workload, deg)
+    solver, info = build_problem(rank, world, n_per_gpu, dtype, a.halo, a.workload, deg, a.geometry)
+    config["geometry"] = ("G streamed (reference data flow)" if a.geometry == "stream" else
+                          f"auto: {solver.nrect} rectilinear + {solver.naff - solver.nrect} affine of {solver.ncells} "
+                          "cells per GPU keep 6 geometric factors instead of 6 n^3")
     config["parallelism"] = (f"block partition x{world}, halo: " +
                              {"p2p": "fused put/get kernels over NVLink peer memory", "nccl": "NCCL send/recv",
                               "none": "none (1 GPU)"}[info["halo"]])
@@ -468,7 +474,17 @@ def main():
     y = torch.zeros(nd, dtype=solver.T, device="cuda")
     D = torch.from_numpy(info["tb"].dphi_1D).cuda()
     tname = "double" if a.dtype == "f64" else "float"
-    if W["nonlinear"]:
+    if a.geometry == "auto":
+        # the solver's own stage-kernel launches (rectilinear / affine / streamed ranges) on its own vectors
+        solver._set_tables()
+        launch = solver._stage_kernel if W["nonlinear"] else solver._stiffness
+        geo = "2" if solver.nrect == nc else ("1" if solver.naff == nc else "mixed")
+        kname = f"stiffness_kernel<{tname},{n},{2 if W['nonlinear'] else 0},1,GEO={geo}> (geometry=auto)"
+        nstream = nc - solver.naff
+        per_dof = 4 if W["nonlinear"] else 2
+        bytes_stiff = (nstream * (nd3 * 4 + (7 if W["nonlinear"] else 6) * nd3 * s + s)
+                       + solver.naff * (nd3 * 4 + 8 * s) + per_dof * s * nd)
+    elif W["nonlinear"]:
         # the Westervelt stage kernel: both stiffness terms + the cell-mass pair, one pass over G
         x2 = torch.randn(nd, dtype=solver.T, device="cuda", generator=gen)
         y2 = torch.zeros(nd, dtype=solver.T, device="cuda")
@@ -513,7 +529,7 @@ def main():
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "stiffness_traffic.json")))
         if (n_per_gpu == tr.get("n_per_gpu") and a.dtype == tr.get("dtype") and a.workload == "linear_box"
-                and deg == 4 and world == 1):
+                and deg == 4 and world == 1 and a.geometry == "stream"):
             traffic = tr["dram_bytes_per_launch"]
     except Exception:
         pass
@@ -543,7 +559,7 @@ def main():
     # ---- the operator through the C ABI with HOST buffers (fus_stiffness_host_*): x from pinned
     #      host memory, y back to pinned host memory, both copies inside the call ----
     op_host = None
-    if not W["nonlinear"]:
+    if not W["nonlinear"] and solver.G is not None and a.geometry == "stream":
         xh = torch.randn(nd, dtype=solver.T).pin_memory()
         yh = torch.zeros(nd, dtype=solver.T).pin_memory()
         fh = _lib.fn("fus_stiffness_host", dtype)
@@ -568,7 +584,7 @@ def main():
     # ---- the same steps with geometry="auto" (extra, not the headline): cells with a constant
     #      Jacobian keep 6 geometric factors instead of 6 n^3 (results equal to rounding) ----
     affine = None
-    if not a.no_affine and (world == 1 or info["halo"] == "nccl"):  # (the peer-memory arena holds one solver's vectors)
+    if not a.no_affine and a.geometry == "stream" and (world == 1 or info["halo"] == "nccl"):  # (the peer-memory arena holds one solver's vectors)
         del x, y
         sol2 = info["make_solver"]("auto")
         sol2.use_graph = not a.no_graph
