@@ -343,6 +343,12 @@ def main():
         print(json.dumps(line), flush=True)
         return 0
 
+    # stdout carries exactly one JSON line: anything libraries print there meanwhile (NCCL's
+    # version banner, ...) is sent to stderr by pointing fd 1 at fd 2 until the line is ready
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -629,6 +635,8 @@ def main():
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         else:
             line["cpu_baseline"] = None
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         # Tear-down: ncclCommDestroy blocks while captured graphs still hold NCCL
