@@ -3,10 +3,15 @@ given dof budget on one GPU.  Prints one JSON line per (degree, dtype) with the
 stiffness / mass / fused-stage throughput and the fraction of the measured HBM
 roofline (algorithmic bytes of SURVEY.md section 8d).
 
-    python tools/sweep.py [--dofs 30e6] [--degrees 2,3,4,5,6,7] [--dtypes f64,f32] > profiles/rNN_sweep.jsonl
+    python tools/sweep.py [--dofs 1e6,8e6,30e6,125e6] [--degrees 2,3,4,5,6,7] [--dtypes f64,f32] [--stage] \
+        > profiles/rNN_sweep.jsonl
+
+``--stage`` adds the fused linear RK stage, streamed and with geometry="auto" (rectilinear
+cells on these boxes: 6 factors per cell instead of 6 n^3).
 """
 
 import argparse
+import gc
 import json
 import os
 import sys
@@ -43,18 +48,18 @@ def timeit(f, reps):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--dofs", type=float, default=30e6)
+    ap.add_argument("--dofs", default="30e6", help="comma-separated dof budgets")
     ap.add_argument("--degrees", default="2,3,4,5,6,7")
     ap.add_argument("--dtypes", default="f64,f32")
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--stage", action="store_true", help="also time the fused linear RK stage")
     a = ap.parse_args()
     pk = peak()
-    for P in [int(x) for x in a.degrees.split(",")]:
+    for dofs, P in [(float(d), int(x)) for d in a.dofs.split(",") for x in a.degrees.split(",")]:
         for tag in a.dtypes.split(","):
             dt = np.float64 if tag == "f64" else np.float32
             s = np.dtype(dt).itemsize
-            N = max(2, int(round((a.dofs ** (1.0 / 3.0) - 1) / P)))
+            N = max(2, int(round((dofs ** (1.0 / 3.0) - 1) / P)))
             su = problem.box_setup(P, N, 0.0015 * N, dt)
             n, nd3, nc, nd = P + 1, (P + 1) ** 3, su.mesh.num_cells, su.ndofs
             tdt = torch.float64 if tag == "f64" else torch.float32
@@ -86,8 +91,21 @@ def main():
                 rec.update({"stage_ms": tst * 1e3, "stage_gdofs": nd / tst / 1e9,
                             "stage_frac": sol.stage_bytes() / tst / 1e9 / pk, "steps_per_s": 1.0 / (4 * tst)})
                 del sol
+                sol = problem.linear_solver(su, [2], [3], geometry="auto")
+                sol.init()
+                sol.rk4(0.0, dtm, 3)
+                torch.cuda.synchronize()
+                e0.record()
+                sol.rk4(sol.t, dtm, a.reps)
+                e1.record()
+                torch.cuda.synchronize()
+                tau = e0.elapsed_time(e1) * 1e-3 / (4 * a.reps)
+                rec.update({"auto_stage_ms": tau * 1e3, "auto_stage_gdofs": nd / tau / 1e9,
+                            "auto_rect_cells": sol.nrect, "auto_steps_per_s": 1.0 / (4 * tau)})
+                del sol
             print(json.dumps(rec), flush=True)
-            del su, x, y, c
+            del su, x, y, c, K, D
+            gc.collect()  # solvers hold captured graphs (private pools) through reference cycles
             torch.cuda.empty_cache()
 
 
