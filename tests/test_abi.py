@@ -37,6 +37,19 @@ def test_error_reporting_without_gpu():
     rc = lib.fus_mass_f32(None, None, None, None, None, -1, 8, None)
     assert rc == 100002  # FUS_ERR_BAD_ARGUMENT
     assert lib.fus_axpy_f64(1.0, None, None, 0, None) == 0  # empty vector: no launch
+    # the affine / rectilinear / sampling / compression entry points validate the same way
+    assert lib.fus_stiffness_affine_f64(None, None, None, None, None, None, None, 5, 1, 0, None) == 100001
+    assert lib.fus_stiffness_affine_f32(None, None, None, None, None, None, None, -3, 4, 1, None) == 100002
+    assert lib.fus_stiffness_rect_f64(None, None, None, None, None, None, 5, 8, 0, None) == 100001
+    assert lib.fus_stiffness_westervelt_rect_f32(*([None] * 12), 0, 4, 1, None) == 0  # zero cells: no launch
+    assert lib.fus_set_rect_tables_f64(4, None, None, None) == 100002
+    assert lib.fus_set_rect_tables_f32(9, None, None, None) == 100001
+    assert lib.fus_eval_points_f64(None, None, None, None, None, 0, 4, None) == 0
+    assert lib.fus_eval_points_f32(None, None, None, None, None, 3, 4, None) == 100002  # null pointers
+    assert b"null" in lib.fus_last_error()
+    assert lib.fus_eval_points_f64(None, None, None, None, None, -1, 4, None) == 100002
+    assert lib.fus_compress_geometry_f64(None, None, None, None, None, None, 0, 125, 1e-12, None) == 0
+    assert lib.fus_compress_geometry_f32(None, None, None, None, None, None, 4, 0, 1e-6, None) == 100002
 
 
 def test_product_never_imports_oracle():
