@@ -623,7 +623,13 @@ def main():
         "roofline": roofline,
         "stage_roofline": {"bound": "hbm", "achieved": stage_bytes / stage_t / 1e9, "peak": peak, "unit": "GB/s",
                            "frac": stage_bytes / stage_t / 1e9 / peak,
-                           "algorithmic_bytes_per_stage": stage_bytes, "stage_ms": stage_t * 1e3},
+                           "algorithmic_bytes_per_stage": stage_bytes, "stage_ms": stage_t * 1e3,
+                           "bytes_model": "stage kernel bytes + 10.25 vector passes per stage (what the fused "
+                                          "ping-pong stages move: 9 + 12 + 12 + 8 per step)",
+                           "survey_8d_model": {"algorithmic_bytes_per_stage": solver.stage_bytes_survey(),
+                                               "frac": solver.stage_bytes_survey() / stage_t / 1e9 / peak,
+                                               "note": "SURVEY.md 8(d): 6s + stiffness + 8s per dof, more than "
+                                                       "this implementation moves"}},
         "e2e_operator_host_buffers": op_host,
         "affine_geometry": affine,
         "operators": {("westervelt_stage_kernel_gdofs" if W["nonlinear"] else "stiffness_gdofs"): info["ndofs_local"] / t_stiff / 1e9, "mass_gdofs": info["ndofs_local"] / t_mass / 1e9,

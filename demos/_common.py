@@ -62,13 +62,13 @@ class PlaneSampler:
     def dump(self, solver):
         import numpy as np
 
-        # between steps un == u on the owned dofs (the close kernel opens the next step); its ghost
-        # entries are made current by the stage's own forward halo - scatter_fwd(u_n_d) in the
-        # reference (:566).  Collective: every rank dumps at the same steps.
+        # ghost entries of the solution are made current by the same forward halo the next step
+        # starts with - scatter_fwd(u_n_d) in the reference (:566).  Collective: every rank dumps
+        # at the same steps.
         if solver.halo is not None:
-            solver.halo.forward(solver.un, solver.ku)
+            solver.halo.forward(solver.u, solver.v)
         if self.data is not None:
-            self.data[:, 2] = self.ev.to_host(solver.un)
+            self.data[:, 2] = self.ev.to_host(solver.u)
             with open(os.path.join(self.dir, f"pressure_field_{self.k}_rank{self.rank}.txt"), "a") as f:
                 np.savetxt(f, self.data, fmt="%.8f", delimiter=",")
         self.k += 1

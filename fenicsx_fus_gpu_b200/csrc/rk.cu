@@ -11,6 +11,11 @@
 // Stage algebra (a, b = Butcher coefficients; ku holds vn, "f0: ku = vn"):
 //   open : un = u0 + a dt ku ; vn = v0 + a dt kv ; ku <- vn ; b <- 0
 //   close: kv = b / m ; u += b_i dt ku ; v += b_i dt kv
+// Ping-pong steps (next_mode 3 / 1 / 1 / 4): the first stage of a step takes its input
+// straight from the base state (a_0 = 0: un = u0, vn = v0) and starts the accumulators from
+// it, the last one leaves the new state in the accumulators, and the caller swaps base and
+// accumulator buffers between steps: 9 + 12 + 12 + 8 vector passes per step instead of 4 x 12,
+// same arithmetic bit for bit.
 // Pure HBM streams, 16-byte vector accesses, grid-stride over a few waves.
 
 #include <initializer_list>
@@ -140,9 +145,20 @@ __device__ __forceinline__ void close_body(const CloseArgs<T>& a, long long k) {
   using P = Pack<T, Vec<T>::W>;
   P b = ld<T, VEC>(a.b, k);
   P m = ld<T, VEC>(a.m, k);
-  P ku = ld<T, VEC>(a.ku, k);
-  P u = ld<T, VEC>(a.u, k);
-  P v = ld<T, VEC>(a.v, k);
+  P ku, u, v, u0, v0;
+  if (a.next_mode == 3) {
+    // first stage of a ping-pong step: the accumulators start from the base state (u0, v0),
+    // which is also the stage input (un = u0, vn = ku = v0): nothing else is read
+    u0 = ld<T, VEC>(a.u0, k);
+    v0 = ld<T, VEC>(a.v0, k);
+    ku = v0;
+    u = u0;
+    v = v0;
+  } else {
+    ku = ld<T, VEC>(a.ku, k);
+    u = ld<T, VEC>(a.u, k);
+    v = ld<T, VEC>(a.v, k);
+  }
   P kv, z;
   if constexpr (WEST) {
     P m0 = ld<T, VEC>(a.m0, k);
@@ -160,9 +176,11 @@ __device__ __forceinline__ void close_body(const CloseArgs<T>& a, long long k) {
   st<T, VEC>(a.v, k, v);
   if (a.kv != nullptr) st<T, VEC>(a.kv, k, kv);
   if constexpr (WEST) st<T, VEC>(a.m, k, z);
-  if (a.next_mode == 1) {
-    P u0 = ld<T, VEC>(a.u0, k);
-    P v0 = ld<T, VEC>(a.v0, k);
+  if (a.next_mode == 1 || a.next_mode == 3) {
+    if (a.next_mode == 1) {
+      u0 = ld<T, VEC>(a.u0, k);
+      v0 = ld<T, VEC>(a.v0, k);
+    }
     P un, vn;
 #pragma unroll
     for (int w = 0; w < W; ++w) {
@@ -178,6 +196,8 @@ __device__ __forceinline__ void close_body(const CloseArgs<T>& a, long long k) {
     st<T, VEC>(a.un, k, u);
     st<T, VEC>(a.ku, k, v);
     st<T, VEC>(a.b, k, z);
+  } else if (a.next_mode == 4) {
+    st<T, VEC>(a.b, k, z);  // last stage of a ping-pong step: the accumulators ARE the new state
   }
 }
 
@@ -192,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, 3) rk_close_kernel(const CloseArgs<T
     const long long k = nv * W + i0;
     if (k < a.n) close_body<T, false, WEST>(a, k);
   }
-  if (a.step != nullptr && a.next_mode == 2 && i0 == 0) *a.step += 1;
+  if (a.step != nullptr && (a.next_mode == 2 || a.next_mode == 4) && i0 == 0) *a.step += 1;
 }
 
 // b[dof[i]] += g*src[i] + dg*src2[i] + vn[dof[i]]*absb[i]; the dof list is unique
@@ -251,7 +271,7 @@ template <typename T, bool WEST>
 int close_entry(T* u, T* v, T* u0, T* v0, T* ku, T* kv, T* un, T* b, T* m, const T* m0, T bdt,
                 T adt_next, int next_mode, int64_t n, int64_t* step, void* stream) {
   if (n < 0) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close: n < 0");
-  if (next_mode < 0 || next_mode > 2) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close: next_mode");
+  if (next_mode < 0 || next_mode > 4) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close: next_mode");
   if (next_mode == 0 && kv == nullptr)
     return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close: kv must be stored when not chained");
   if (n == 0) return 0;

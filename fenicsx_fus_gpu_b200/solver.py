@@ -18,7 +18,11 @@ synchronisations and 3-5 host-staged MPI rounds becomes
     close  (b/m, u,v updates, next stage's un/vn, b = 0  - ONE pass over the vectors)
 
 i.e. 3 launches per stage on one GPU, no host synchronisation, and a whole
-time step (4 stages) is captured once as a CUDA graph and replayed.  Source
+time step (4 stages) is captured once as a CUDA graph and replayed.  Steps
+"ping-pong": the first stage reads the base state directly (a_0 = 0), the last
+one leaves the new state in the accumulators, and base / accumulator buffers
+swap roles between steps (two graphs, replayed alternately) - 41 vector passes
+per step instead of 48, same arithmetic bit for bit.  Source
 amplitudes come from a device table indexed by a device step counter, so a
 replay needs no host work at all.
 
@@ -121,9 +125,11 @@ class _RK4:
         self.nupd = int(halo.N) if self.p2p else self.ndofs  # entries the vector kernels update
         zx = halo.alloc if self.p2p else z
         # the reference's 14 vectors (cuda/demo_linear_box.py:380-385, 464-471)
-        # shrink to 9: u v u0 v0 ku kv un b m  (vn lives in ku; g, u_n, v_n fused away)
-        self.u, self.v, self.u0, self.v0 = z(), z(), z(), z()
-        self.kv = z()
+        # shrink to 8: two (u, v) pairs that alternate between "base state of this step" and
+        # "accumulator" (= the next step's base), ku un b m  (vn lives in ku; g, u_n, v_n,
+        # kv fused away).  The base pair is the stage-0 input, so it is halo-exchanged too.
+        self._uv = [(zx(), zx()), (zx(), zx())]
+        self._parity = 0  # _uv[_parity] is the base state (the solution between steps)
         self.ku, self.un, self.b = zx(), zx(), zx()
         self.m = zx()
         self._zx = zx
@@ -131,7 +137,7 @@ class _RK4:
         self.gtab = None
         self.t = 0.0
         self.nstep = 0
-        self._graph = None
+        self._graph = None  # [graph of a step with parity 0, with parity 1]
         self._graph_dt = None
         self._graph_tab = None
         self.graph_error = None
@@ -152,6 +158,15 @@ class _RK4:
         self.naff = 0  # cells [0, naff) are affine: [nrect, naff) go through the general affine kernel
         self.Gc = self.detJc = None
         self._rect_tables = None
+
+    # the solution between steps (device tensors; write initial data into them before rk4)
+    @property
+    def u(self):
+        return self._uv[self._parity][0]
+
+    @property
+    def v(self):
+        return self._uv[self._parity][1]
 
     # ---- set-up helpers ------------------------------------------------------
     def _set_tables(self):
@@ -265,28 +280,25 @@ class _RK4:
     def _ptr(self, t):
         return None if t is None else t.data_ptr()
 
-    def _boundary(self, stage, g, dg, use_table):
+    def _boundary(self, stage, g, dg, use_table, vn):
         nb = int(self._bdofs.numel())
         if not nb:
             return
         check(fn("fus_boundary_terms", self.dtype)(
-            self.b.data_ptr(), self.ku.data_ptr(), self._bdofs.data_ptr(), self._ptr(self._src),
+            self.b.data_ptr(), vn.data_ptr(), self._bdofs.data_ptr(), self._ptr(self._src),
             self._ptr(self._src2), self._ptr(self._absb), float(g), float(dg),
             self.gtab.data_ptr() if use_table else None,
             self.step_dev.data_ptr() if use_table else None, 8, 2 * stage, nb, current_stream()),
             "fus_boundary_terms")
 
     def _open_first(self):
-        """u0 = u, v0 = v, un = u0, vn(=ku) = v0, b = 0  (cuda/demo_linear_box.py:491-508 at a_0 = 0)."""
-        self.ku.zero_()
-        self.kv.zero_()
-        check(fn("fus_rk_open", self.dtype)(
-            self.u.data_ptr(), self.v.data_ptr(), self.u0.data_ptr(), self.v0.data_ptr(),
-            self.ku.data_ptr(), self.kv.data_ptr(), self.un.data_ptr(), self.b.data_ptr(), 0.0, 1,
-            self.nupd, current_stream()), "fus_rk_open")
+        """b = 0 before the first stage (cuda/demo_linear_box.py:541); the stage-0 input is the
+        base state itself (:491-508 at a_0 = 0: un = u0, vn = v0), nothing is copied."""
+        self.b.zero_()
+        if self.westervelt:
+            self.m.zero_()
         if self.p2p:
-            self._zero_ghosts()
-            self.halo.barrier()  # nobody's first put may land before this rank's open has run
+            self.halo.barrier()  # nobody's first put may land before this rank is set up
         self._opened = True
 
     def _zero_ghosts(self):
@@ -299,15 +311,15 @@ class _RK4:
             if self.westervelt:
                 check(fn("fus_fill", self.dtype)(0.0, self.m.data_ptr() + off, ng, current_stream()), "fus_fill")
 
-    def _assemble(self, stage, g, dg, use_table):  # pragma: no cover - abstract
+    def _assemble(self, stage, g, dg, use_table, x, vn):  # pragma: no cover - abstract
         raise NotImplementedError
 
-    def _close(self, stage, dt, count_step):  # pragma: no cover - abstract
+    def _close(self, stage, dt, count_step, base, acc):  # pragma: no cover - abstract
         raise NotImplementedError
 
-    def _halo_forward(self):
+    def _halo_forward(self, x, vn):
         if self.halo is not None:
-            self.halo.forward(self.un, self.ku)
+            self.halo.forward(x, vn)
 
     def _halo_reverse(self):
         if self.halo is not None:
@@ -316,22 +328,36 @@ class _RK4:
             else:
                 self.halo.reverse(self.b)
 
-    def _enqueue_step(self, dt, t, use_table):
+    def _enqueue_step(self, dt, t, use_table, parity=None):
+        """The launches of one RK4 step whose base state is ``_uv[parity]`` (default: the current
+        one); the new state is left in ``_uv[1 - parity]``.  Does not flip ``_parity``."""
+        parity = self._parity if parity is None else parity
+        base, acc = self._uv[parity], self._uv[1 - parity]
         for i in range(4):
             g = dg = 0.0
             if not use_table and self.source is not None:
                 g, dg = self.source(t + C_RUNGE[i] * dt if self.source_at_stage_time else t)
-            self._halo_forward()
-            self._assemble(i, g, dg, use_table)
+            # stage input: the base state itself in stage 0 (a_0 = 0), un / vn (= ku) afterwards
+            x, vn = base if i == 0 else (self.un, self.ku)
+            self._halo_forward(x, vn)
+            self._assemble(i, g, dg, use_table, x, vn)
             self._halo_reverse()
-            self._close(i, dt, use_table)
+            self._close(i, dt, use_table, base, acc)
             if self.p2p:
                 self._zero_ghosts()
+
+    def _close_args(self, stage, dt, base, acc):
+        """(u, v, u0, v0 pointers, bdt, adt_next, next_mode) of the close kernel for ``stage``:
+        3 = first stage of a ping-pong step, 1 = chained, 4 = last stage."""
+        mode = 3 if stage == 0 else (4 if stage == 3 else 1)
+        adt = 0.0 if stage == 3 else A_RUNGE[stage + 1] * dt
+        return (acc[0].data_ptr(), acc[1].data_ptr(), base[0].data_ptr(), base[1].data_ptr(),
+                B_RUNGE[stage] * dt, adt, mode)
 
     # ---- public --------------------------------------------------------------
     def init(self):
         """Zero initial state (cpp/common/Linear.hpp:146-154)."""
-        for t in (self.u, self.v, self.u0, self.v0, self.ku, self.kv, self.un, self.b):
+        for t in (*self._uv[0], *self._uv[1], self.ku, self.un, self.b):
             t.zero_()
         self.t = 0.0
         self.nstep = 0
@@ -370,6 +396,7 @@ class _RK4:
         else:
             for k in range(nsteps):
                 self._enqueue_step(dt, 0.0, True)
+                self._parity ^= 1
         for _ in range(nsteps):
             self.t += dt
         self.nstep += nsteps
@@ -391,6 +418,7 @@ class _RK4:
         if not self._opened:
             self._open_first()
         self._enqueue_step(dt, self.t, False)
+        self._parity ^= 1
         self.t += dt
         self.nstep += 1
         return self.t
@@ -399,16 +427,18 @@ class _RK4:
         """One RK4 step reading the source table row ``step_dev`` points at: a
         graph replay (or, when capture is unavailable, the same launches eagerly)."""
         if self._graph is not None:
-            self._graph.replay()
+            self._graph[self._parity].replay()
         else:
             self._enqueue_step(dt, 0.0, True)
+        self._parity ^= 1
 
     def _capture(self, dt):
         torch = _torch()
         # warm up outside capture (lazy NCCL communicators, module loading)
         saved = [t.clone() for t in self._state()]
         step0 = self.step_dev.clone()
-        self._enqueue_step(dt, 0.0, True)
+        for parity in (self._parity, 1 - self._parity):  # both buffer roles (halo peer tables are built lazily)
+            self._enqueue_step(dt, 0.0, True, parity)
         torch.cuda.synchronize()
         for t, s in zip(self._state(), saved):
             t.copy_(s)
@@ -417,17 +447,20 @@ class _RK4:
             self.halo.barrier()  # every rank has restored its ghost slots before anyone's next put
         self._graph_dt, self._graph_tab = dt, self.gtab.data_ptr()
         try:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._enqueue_step(dt, 0.0, True)
-            self._graph = g  # capture does not execute: state is still the saved one
+            graphs = []
+            for parity in (0, 1):  # base / accumulator buffers swap roles every step
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue_step(dt, 0.0, True, parity)
+                graphs.append(g)
+            self._graph = graphs  # capture does not execute: state is still the saved one
         except Exception as e:  # e.g. a transport that cannot be captured
             self._graph = None
             self.graph_error = repr(e)
             torch.cuda.synchronize()
 
     def _state(self):
-        return [self.u, self.v, self.u0, self.v0, self.ku, self.kv, self.un, self.b, self.m]
+        return [*self._uv[0], *self._uv[1], self.ku, self.un, self.b, self.m]
 
     # algorithmic HBM bytes of one RK stage
     def stage_bytes(self):
@@ -435,7 +468,12 @@ class _RK4:
         Nd = self.n**3
         nstream = self.ncells - self.naff
         stiff = nstream * (Nd * 4 + 6 * Nd * s + s) + self.naff * (Nd * 4 + 7 * s) + 2 * s * self.ndofs
-        return stiff + 14 * s * self.ndofs
+        # vector passes of the close kernels per step: 9 + 12 + 12 + 8 (ping-pong), i.e. 10.25 a stage
+        return stiff + 10.25 * s * self.ndofs
+
+    def stage_bytes_survey(self):
+        """SURVEY.md section 8(d)'s model of a fused linear stage: 6s + stiffness + 8s per dof."""
+        return self.stage_bytes() + (14 - 10.25) * self.dtype.itemsize * self.ndofs
 
 
 class LinearSpectral3D(_RK4):
@@ -474,36 +512,35 @@ class LinearSpectral3D(_RK4):
         self._boundary_setup(terms)
         self._setup_geometry(None, ["cell_coeff2"])
 
-    def _stiffness(self):
+    def _stiffness(self, x=None):
+        x = self.un if x is None else x
         nr, na, nc, st = self.nrect, self.naff, self.ncells, current_stream()
         if nr:  # rectilinear cells: three decoupled 1-D stiffness products
             check(fn("fus_stiffness_rect", self.dtype)(
-                self.un.data_ptr(), self.cell_coeff2.data_ptr(), self.b.data_ptr(), self.Gc.data_ptr(),
+                x.data_ptr(), self.cell_coeff2.data_ptr(), self.b.data_ptr(), self.Gc.data_ptr(),
                 self.dofmap.data_ptr(), None, nr, self.P, FUS_TABLES_RESIDENT, st), "fus_stiffness_rect")
         if na > nr:  # affine cells: 6 factors per cell, nothing streamed but the dofmap
             check(fn("fus_stiffness_affine", self.dtype)(
-                self.un.data_ptr(), self.cell_coeff2[nr:].data_ptr(), self.b.data_ptr(), self.Gc[nr:].data_ptr(),
+                x.data_ptr(), self.cell_coeff2[nr:].data_ptr(), self.b.data_ptr(), self.Gc[nr:].data_ptr(),
                 self._weights.data_ptr(), self.dofmap[nr:].data_ptr(), None, na - nr, self.P,
                 FUS_TABLES_RESIDENT, st), "fus_stiffness_affine")
         if na < nc:
             check(fn("fus_stiffness", self.dtype)(
-                self.un.data_ptr(), self.cell_coeff2[na:].data_ptr(), self.b.data_ptr(), self.G.data_ptr(),
+                x.data_ptr(), self.cell_coeff2[na:].data_ptr(), self.b.data_ptr(), self.G.data_ptr(),
                 self.dofmap[na:].data_ptr(), None, nc - na, self.P, FUS_TABLES_RESIDENT, st),
                 "fus_stiffness")
 
-    def _assemble(self, stage, g, dg, use_table):
+    def _assemble(self, stage, g, dg, use_table, x, vn):
         # b += K(-1/rho; un)                                  (cuda/demo_linear_box.py:543-545)
-        self._probed(self._stiffness)
+        self._probed(lambda: self._stiffness(x))
         # b += g * src + vn * absb                            (:546-551)
-        self._boundary(stage, g, dg, use_table)
+        self._boundary(stage, g, dg, use_table, vn)
 
-    def _close(self, stage, dt, count_step):
-        last = stage == 3
+    def _close(self, stage, dt, count_step, base, acc):
+        u, v, u0, v0, bdt, adt, mode = self._close_args(stage, dt, base, acc)
         check(fn("fus_rk_close", self.dtype)(
-            self.u.data_ptr(), self.v.data_ptr(), self.u0.data_ptr(), self.v0.data_ptr(),
-            self.ku.data_ptr(), None, self.un.data_ptr(), self.b.data_ptr(), self.m.data_ptr(),
-            B_RUNGE[stage] * dt, 0.0 if last else A_RUNGE[stage + 1] * dt, 2 if last else 1,
-            self.nupd, self.step_dev.data_ptr() if count_step else None, current_stream()),
+            u, v, u0, v0, self.ku.data_ptr(), None, self.un.data_ptr(), self.b.data_ptr(), self.m.data_ptr(),
+            bdt, adt, mode, self.nupd, self.step_dev.data_ptr() if count_step else None, current_stream()),
             "fus_rk_close")
 
 
@@ -558,42 +595,42 @@ class WesterveltSpectral3D(_RK4):
     def _state(self):
         return super()._state() + [self.m0]
 
-    def _assemble(self, stage, g, dg, use_table):
+    def _assemble(self, stage, g, dg, use_table, x, vn):
         # b += K(c3; un) + K(c4; vn) + M(c5; vn^2) and m += M(c2; un): ONE pass over G, detJ
         # and the dofmap, un / vn gathered once                    (:609-612, :620-628)
-        self._probed(self._stage_kernel)
+        self._probed(lambda: self._stage_kernel(x, vn))
         # b += g*src + dg*src2 + vn*absb                                      (:629-639)
-        self._boundary(stage, g, dg, use_table)
+        self._boundary(stage, g, dg, use_table, vn)
 
-    def _stage_kernel(self):
+    def _stage_kernel(self, x=None, vn=None):
+        x = self.un if x is None else x
+        vn = self.ku if vn is None else vn
         nr, na, nc, st = self.nrect, self.naff, self.ncells, current_stream()
         if nr:
             check(fn("fus_stiffness_westervelt_rect", self.dtype)(
-                self.un.data_ptr(), self.c3.data_ptr(), self.ku.data_ptr(), self.c4.data_ptr(),
+                x.data_ptr(), self.c3.data_ptr(), vn.data_ptr(), self.c4.data_ptr(),
                 self.c2.data_ptr(), self.c5.data_ptr(), self.m.data_ptr(), self.b.data_ptr(),
                 self.Gc.data_ptr(), self.detJc.data_ptr(), self.dofmap.data_ptr(), None, nr, self.P,
                 FUS_TABLES_RESIDENT, st), "fus_stiffness_westervelt_rect")
         if na > nr:
             check(fn("fus_stiffness_westervelt_affine", self.dtype)(
-                self.un.data_ptr(), self.c3[nr:].data_ptr(), self.ku.data_ptr(), self.c4[nr:].data_ptr(),
+                x.data_ptr(), self.c3[nr:].data_ptr(), vn.data_ptr(), self.c4[nr:].data_ptr(),
                 self.c2[nr:].data_ptr(), self.c5[nr:].data_ptr(), self.m.data_ptr(), self.b.data_ptr(),
                 self.Gc[nr:].data_ptr(), self.detJc[nr:].data_ptr(), self._weights.data_ptr(),
                 self.dofmap[nr:].data_ptr(), None, na - nr, self.P, FUS_TABLES_RESIDENT, st),
                 "fus_stiffness_westervelt_affine")
         if na < nc:
             check(fn("fus_stiffness_westervelt", self.dtype)(
-                self.un.data_ptr(), self.c3[na:].data_ptr(), self.ku.data_ptr(), self.c4[na:].data_ptr(),
+                x.data_ptr(), self.c3[na:].data_ptr(), vn.data_ptr(), self.c4[na:].data_ptr(),
                 self.c2[na:].data_ptr(), self.c5[na:].data_ptr(), self.m.data_ptr(), self.b.data_ptr(),
                 self.G.data_ptr(), self.detJ.data_ptr(), self.dofmap[na:].data_ptr(), None, nc - na, self.P,
                 FUS_TABLES_RESIDENT, st), "fus_stiffness_westervelt")
 
-    def _close(self, stage, dt, count_step):
-        last = stage == 3
+    def _close(self, stage, dt, count_step, base, acc):
+        u, v, u0, v0, bdt, adt, mode = self._close_args(stage, dt, base, acc)
         check(fn("fus_rk_close_westervelt", self.dtype)(
-            self.u.data_ptr(), self.v.data_ptr(), self.u0.data_ptr(), self.v0.data_ptr(),
-            self.ku.data_ptr(), None, self.un.data_ptr(), self.b.data_ptr(), self.m.data_ptr(),
-            self.m0.data_ptr(), B_RUNGE[stage] * dt, 0.0 if last else A_RUNGE[stage + 1] * dt,
-            2 if last else 1, self.nupd, self.step_dev.data_ptr() if count_step else None,
+            u, v, u0, v0, self.ku.data_ptr(), None, self.un.data_ptr(), self.b.data_ptr(), self.m.data_ptr(),
+            self.m0.data_ptr(), bdt, adt, mode, self.nupd, self.step_dev.data_ptr() if count_step else None,
             current_stream()), "fus_rk_close_westervelt")
 
     def stage_bytes(self):

@@ -259,9 +259,17 @@ int fus_rk_open_f32(const float* u, const float* v, float* u0, float* v0, float*
  *   next_mode 1: un = u0 + adt_next*ku ; ku' = v0 + adt_next*kv ; b = 0
  *   next_mode 2: (step boundary) u0 = u ; v0 = v ; un = u ; ku' = v ; b = 0
  *   next_mode 0: nothing more
- * kv is stored when non-NULL; it may be NULL in modes 1 and 2 (nothing reads
+ *   next_mode 3: (first stage of a "ping-pong" step) u, v, ku are NOT read: the stage input was
+ *                the base state itself (a_0 = 0: un = u0, vn = v0), so
+ *                u = u0 + bdt*v0 ; v = v0 + bdt*kv ; un = u0 + adt_next*v0 ;
+ *                ku' = v0 + adt_next*kv ; b = 0
+ *   next_mode 4: (last stage of a ping-pong step) b = 0 and nothing else: the accumulators
+ *                u, v ARE the new state; the caller swaps (u, v) with (u0, v0) between steps.
+ *                A step run as 3 / 1 / 1 / 4 makes 9 + 12 + 12 + 8 vector passes instead of
+ *                the 4 x 12 of 1 / 1 / 1 / 2, with the same arithmetic bit for bit.
+ * kv is stored when non-NULL; it may be NULL in modes 1-4 (nothing reads
  * it again).  step_dev (may be NULL) is a device step counter incremented in
- * mode 2 - it indexes the source table of fus_boundary_terms, so a whole RK
+ * modes 2 and 4 - it indexes the source table of fus_boundary_terms, so a whole RK
  * step can be replayed as a CUDA graph with no host work. */
 int fus_rk_close_f64(double* u, double* v, double* u0, double* v0, double* ku, double* kv,
                      double* un, double* b, const double* m, double bdt, double adt_next,
