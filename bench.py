@@ -485,26 +485,18 @@ def main():
         solver._set_tables()
         launch = solver._stage_kernel if W["nonlinear"] else solver._stiffness
         geo = "2" if solver.nrect == nc else ("1" if solver.naff == nc else "mixed")
-        kname = f"stiffness_kernel<{tname},{n},{2 if W['nonlinear'] else 0},1,GEO={geo}> (geometry=auto)"
+        kname = f"stiffness_kernel<{tname},{n},{1 if W['nonlinear'] else 0},1,GEO={geo}> (geometry=auto)"
         nstream = nc - solver.naff
-        per_dof = 4 if W["nonlinear"] else 2
-        bytes_stiff = (nstream * (nd3 * 4 + (7 if W["nonlinear"] else 6) * nd3 * s + s)
-                       + solver.naff * (nd3 * 4 + 8 * s) + per_dof * s * nd)
+        per_dof = 3 if W["nonlinear"] else 2
+        bytes_stiff = nstream * (nd3 * 4 + 6 * nd3 * s + 2 * s) + solver.naff * (nd3 * 4 + 8 * s) + per_dof * s * nd
     elif W["nonlinear"]:
-        # the Westervelt stage kernel: both stiffness terms + the cell-mass pair, one pass over G
-        x2 = torch.randn(nd, dtype=solver.T, device="cuda", generator=gen)
-        y2 = torch.zeros(nd, dtype=solver.T, device="cuda")
-        fw = _lib.fn("fus_stiffness_westervelt", dtype)
-        st = torch.cuda.current_stream().cuda_stream
-
-        def launch():
-            rc = fw(x.data_ptr(), solver.c3.data_ptr(), x2.data_ptr(), solver.c4.data_ptr(), solver.c2.data_ptr(),
-                    solver.c5.data_ptr(), y2.data_ptr(), y.data_ptr(), solver.G.data_ptr(), solver.detJ.data_ptr(),
-                    solver.dofmap.data_ptr(), D.data_ptr(), nc, deg, 0, st)
-            assert rc == 0
-        kname = f"stiffness_kernel<{tname},{n},2,1> (fus_stiffness_westervelt_{a.dtype})"
-        # per cell: dofmap + G + detJ + 4 coefficients; per dof: read un, vn, write b, m
-        bytes_stiff = nc * (nd3 * 4 + 6 * nd3 * s + nd3 * s + 4 * s) + 4 * s * nd
+        # the Westervelt stage kernel: both stiffness terms in one pass over G (the cell-mass pair is
+        # pointwise in the close kernel), launched as the solver launches it, on its own vectors
+        solver._set_tables()
+        launch = solver._stage_kernel
+        kname = f"stiffness_kernel<{tname},{n},1,1,0> (fus_stiffness2_{a.dtype}: K(c3; un) + K(c4; vn))"
+        # per cell: dofmap + G + 2 coefficients; per dof: read un, vn, write b
+        bytes_stiff = nc * (nd3 * 4 + 6 * nd3 * s + 2 * s) + 3 * s * nd
     else:
         K = ops.stiffness_operator(deg, dtype)
 

@@ -34,6 +34,9 @@ def _sigs():
         "fus_set_rect_tables": [I, P, P, P],
         "fus_stiffness_rect": [P, P, P, P, P, P, L, I, I, P],
         "fus_stiffness_westervelt_rect": [P, P, P, P, P, P, P, P, P, P, P, P, L, I, I, P],
+        "fus_stiffness2_affine": [P, P, P, P, P, P, P, P, P, L, I, I, P],
+        "fus_stiffness2_rect": [P, P, P, P, P, P, P, P, L, I, I, P],
+        "fus_rk_close_westervelt_pw": [P, P, P, P, P, P, P, P, P, P, P, T, T, I, L, P, P],
         "fus_compress_geometry": [P, P, P, P, P, P, L, I, T, P],
         "fus_mass": [P, P, P, P, P, L, I, P],
         "fus_axpy": [T, P, P, L, P],

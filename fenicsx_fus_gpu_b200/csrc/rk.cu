@@ -132,6 +132,8 @@ struct CloseArgs {
   T* b;
   T* m;         // Westervelt: state-dependent part, zeroed here; linear: the lumped mass (read only)
   const T* m0;  // Westervelt only
+  const T* m2;  // pointwise Westervelt (WEST == 2): lumped M(c2; 1) and M(c5; 1)
+  const T* m5;
   T bdt;
   T adt_next;
   int next_mode;
@@ -139,12 +141,22 @@ struct CloseArgs {
   long long* step;  // device step counter, incremented at a step boundary (may be null)
 };
 
-template <typename T, bool VEC, bool WEST>
+// WEST 0: linear (kv = b / m).  WEST 1: m += m0, kv = b / m, m = 0 (the cell-mass pair was
+// accumulated into m and b by the stage kernel).  WEST 2: the lumped mass is diagonal, so the
+// cell-mass pair of cuda/demo_nonlinear_bowl.py:609-612, 626-628 is pointwise:
+//   M(c2; un) = un * M(c2; 1) = un * m2,   M(c5; vn^2) = vn^2 * m5
+// and kv = (b + vn^2 m5) / (m0 + un m2) with un, vn the stage input (un still holds it here).
+template <typename T, bool VEC, int WEST>
 __device__ __forceinline__ void close_body(const CloseArgs<T>& a, long long k) {
   constexpr int W = VEC ? Vec<T>::W : 1;
   using P = Pack<T, Vec<T>::W>;
   P b = ld<T, VEC>(a.b, k);
-  P m = ld<T, VEC>(a.m, k);
+  P m;
+  if constexpr (WEST == 2) {
+    m = ld<T, VEC>(a.m0, k);
+  } else {
+    m = ld<T, VEC>(a.m, k);
+  }
   P ku, u, v, u0, v0;
   if (a.next_mode == 3) {
     // first stage of a ping-pong step: the accumulators start from the base state (u0, v0),
@@ -160,10 +172,25 @@ __device__ __forceinline__ void close_body(const CloseArgs<T>& a, long long k) {
     v = ld<T, VEC>(a.v, k);
   }
   P kv, z;
-  if constexpr (WEST) {
+  if constexpr (WEST == 1) {
     P m0 = ld<T, VEC>(a.m0, k);
 #pragma unroll
     for (int w = 0; w < W; ++w) m.v[w] = m.v[w] + m0.v[w];  // axpy(1.0, m0, m)
+  }
+  if constexpr (WEST == 2) {
+    const P m2 = ld<T, VEC>(a.m2, k);
+    const P m5 = ld<T, VEC>(a.m5, k);
+    P xin;  // the stage input un: the base state itself in the first stage of a ping-pong step
+    if (a.next_mode == 3) {
+      xin = u0;
+    } else {
+      xin = ld<T, VEC>(a.un, k);
+    }
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      m.v[w] = xin.v[w] * m2.v[w] + m.v[w];                 // m = m0 + M(c2; un)
+      b.v[w] = (ku.v[w] * ku.v[w]) * m5.v[w] + b.v[w];      // b += M(c5; vn^2)
+    }
   }
 #pragma unroll
   for (int w = 0; w < W; ++w) {
@@ -175,7 +202,7 @@ __device__ __forceinline__ void close_body(const CloseArgs<T>& a, long long k) {
   st<T, VEC>(a.u, k, u);
   st<T, VEC>(a.v, k, v);
   if (a.kv != nullptr) st<T, VEC>(a.kv, k, kv);
-  if constexpr (WEST) st<T, VEC>(a.m, k, z);
+  if constexpr (WEST == 1) st<T, VEC>(a.m, k, z);
   if (a.next_mode == 1 || a.next_mode == 3) {
     if (a.next_mode == 1) {
       u0 = ld<T, VEC>(a.u0, k);
@@ -201,7 +228,7 @@ __device__ __forceinline__ void close_body(const CloseArgs<T>& a, long long k) {
   }
 }
 
-template <typename T, bool VEC, bool WEST>
+template <typename T, bool VEC, int WEST>
 __global__ void __launch_bounds__(kThreads, 3) rk_close_kernel(const CloseArgs<T> a) {
   constexpr int W = VEC ? Vec<T>::W : 1;
   const long long stride = (long long)gridDim.x * kThreads;
@@ -267,18 +294,21 @@ int open_entry(const T* u, const T* v, T* u0, T* v0, T* ku, const T* kv, T* un, 
   return 0;
 }
 
-template <typename T, bool WEST>
+template <typename T, int WEST>
 int close_entry(T* u, T* v, T* u0, T* v0, T* ku, T* kv, T* un, T* b, T* m, const T* m0, T bdt,
-                T adt_next, int next_mode, int64_t n, int64_t* step, void* stream) {
+                T adt_next, int next_mode, int64_t n, int64_t* step, void* stream,
+                const T* m2 = nullptr, const T* m5 = nullptr) {
   if (n < 0) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close: n < 0");
   if (next_mode < 0 || next_mode > 4) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close: next_mode");
   if (next_mode == 0 && kv == nullptr)
     return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close: kv must be stored when not chained");
   if (n == 0) return 0;
-  CloseArgs<T> a{u, v, u0, v0, ku, kv, un, b, m, m0, bdt, adt_next, next_mode, n,
+  if (WEST == 2 && (m0 == nullptr || m2 == nullptr || m5 == nullptr))
+    return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close_westervelt_pw: null m0 / m2 / m5");
+  CloseArgs<T> a{u, v, u0, v0, ku, kv, un, b, m, m0, m2, m5, bdt, adt_next, next_mode, n,
                  reinterpret_cast<long long*>(step)};
   cudaStream_t st_ = static_cast<cudaStream_t>(stream);
-  if (aligned16({u, v, u0, v0, ku, kv, un, b, m, m0})) {
+  if (aligned16({u, v, u0, v0, ku, kv, un, b, m, m0, m2, m5})) {
     rk_close_kernel<T, true, WEST><<<grid_for(n / Vec<T>::W + 1), kThreads, 0, st_>>>(a);
   } else {
     rk_close_kernel<T, false, WEST><<<grid_for(n), kThreads, 0, st_>>>(a);
@@ -311,14 +341,20 @@ extern "C" {
   }                                                                                              \
   int fus_rk_close_##SFX(T* u, T* v, T* u0, T* v0, T* ku, T* kv, T* un, T* b, const T* m, T bdt, \
                          T adt_next, int next_mode, int64_t n, int64_t* step_dev, void* s) {     \
-    return close_entry<T, false>(u, v, u0, v0, ku, kv, un, b, const_cast<T*>(m), nullptr, bdt,   \
+    return close_entry<T, 0>(u, v, u0, v0, ku, kv, un, b, const_cast<T*>(m), nullptr, bdt,       \
                                  adt_next, next_mode, n, step_dev, s);                           \
   }                                                                                              \
   int fus_rk_close_westervelt_##SFX(T* u, T* v, T* u0, T* v0, T* ku, T* kv, T* un, T* b, T* m,   \
                                     const T* m0, T bdt, T adt_next, int next_mode, int64_t n,    \
                                     int64_t* step_dev, void* s) {                                \
-    return close_entry<T, true>(u, v, u0, v0, ku, kv, un, b, m, m0, bdt, adt_next, next_mode, n, \
-                                step_dev, s);                                                    \
+    return close_entry<T, 1>(u, v, u0, v0, ku, kv, un, b, m, m0, bdt, adt_next, next_mode, n,    \
+                             step_dev, s);                                                       \
+  }                                                                                              \
+  int fus_rk_close_westervelt_pw_##SFX(T* u, T* v, T* u0, T* v0, T* ku, T* kv, T* un, T* b,      \
+                                       const T* m0, const T* m2, const T* m5, T bdt, T adt_next, \
+                                       int next_mode, int64_t n, int64_t* step_dev, void* s) {   \
+    return close_entry<T, 2>(u, v, u0, v0, ku, kv, un, b, nullptr, m0, bdt, adt_next, next_mode, \
+                             n, step_dev, s, m2, m5);                                            \
   }                                                                                              \
   int fus_boundary_terms_##SFX(T* b, const T* vn, const int32_t* dof, const T* src,              \
                                const T* src2, const T* absb, T g, T dg, const T* gtab,           \

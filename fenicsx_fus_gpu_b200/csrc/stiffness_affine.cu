@@ -68,6 +68,7 @@ int affine_entry(const T* xa, const T* ca, const T* xb, const T* cb, T* y, const
     if (detJc == nullptr) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "stiffness_westervelt_affine: null detJc");
     return geo == 2 ? launch<T, 2, 2>(a, P, flags, st) : launch<T, 2, 1>(a, P, flags, st);
   }
+  if (mode == 1) return geo == 2 ? launch<T, 1, 2>(a, P, flags, st) : launch<T, 1, 1>(a, P, flags, st);
   return geo == 2 ? launch<T, 0, 2>(a, P, flags, st) : launch<T, 0, 1>(a, P, flags, st);
 }
 
@@ -217,6 +218,29 @@ int fus_stiffness_westervelt_rect_f32(const float* un, const float* c3, const fl
                                       int flags, void* stream) {
   return affine_entry<float>(un, c3, vn, c4, b, Gc, nullptr, dofmap, dphi, ncells, P, flags, stream, 2,
                              detJc, c2, c5, m, 2);
+}
+
+int fus_stiffness2_affine_f64(const double* xa, const double* ca, const double* xb, const double* cb,
+                              double* y, const double* Gc, const double* wq, const int32_t* dofmap,
+                              const double* dphi, int64_t ncells, int P, int flags, void* stream) {
+  return affine_entry<double>(xa, ca, xb, cb, y, Gc, wq, dofmap, dphi, ncells, P, flags, stream, 1);
+}
+int fus_stiffness2_affine_f32(const float* xa, const float* ca, const float* xb, const float* cb,
+                              float* y, const float* Gc, const float* wq, const int32_t* dofmap,
+                              const float* dphi, int64_t ncells, int P, int flags, void* stream) {
+  return affine_entry<float>(xa, ca, xb, cb, y, Gc, wq, dofmap, dphi, ncells, P, flags, stream, 1);
+}
+int fus_stiffness2_rect_f64(const double* xa, const double* ca, const double* xb, const double* cb,
+                            double* y, const double* Gc, const int32_t* dofmap, const double* dphi,
+                            int64_t ncells, int P, int flags, void* stream) {
+  return affine_entry<double>(xa, ca, xb, cb, y, Gc, nullptr, dofmap, dphi, ncells, P, flags, stream,
+                              1, nullptr, nullptr, nullptr, nullptr, 2);
+}
+int fus_stiffness2_rect_f32(const float* xa, const float* ca, const float* xb, const float* cb,
+                            float* y, const float* Gc, const int32_t* dofmap, const float* dphi,
+                            int64_t ncells, int P, int flags, void* stream) {
+  return affine_entry<float>(xa, ca, xb, cb, y, Gc, nullptr, dofmap, dphi, ncells, P, flags, stream, 1,
+                             nullptr, nullptr, nullptr, nullptr, 2);
 }
 
 int fus_compress_geometry_f64(const double* G, const double* detJ, const double* wq, double* Gc,

@@ -523,7 +523,7 @@ class P2PHaloExchange:
         self._ptrs = (C.c_void_p * 4)()
 
     @staticmethod
-    def arena_bytes(ndofs_local: int, float_type, nvec: int = 10) -> int:
+    def arena_bytes(ndofs_local: int, float_type, nvec: int = 12) -> int:
         """Arena size for ``nvec`` exchanged vectors of ``ndofs_local`` entries."""
         return nvec * ((int(ndofs_local) * np.dtype(float_type).itemsize + 255) // 256 * 256 + 256)
 

@@ -121,6 +121,7 @@ class _RK4:
         # With the peer-memory halo (scatterer.P2PHaloExchange) the exchanged vectors live in
         # peer-addressable memory and only their owned part is updated locally: the ghost
         # slots are written by the neighbours.
+        self._m_accum = False  # Westervelt "cells" form: m is accumulated per stage (and reverse-exchanged)
         self.p2p = bool(getattr(halo, "p2p", False))
         self.nupd = int(halo.N) if self.p2p else self.ndofs  # entries the vector kernels update
         zx = halo.alloc if self.p2p else z
@@ -295,7 +296,7 @@ class _RK4:
         """b = 0 before the first stage (cuda/demo_linear_box.py:541); the stage-0 input is the
         base state itself (:491-508 at a_0 = 0: un = u0, vn = v0), nothing is copied."""
         self.b.zero_()
-        if self.westervelt:
+        if self._m_accum:
             self.m.zero_()
         if self.p2p:
             self.halo.barrier()  # nobody's first put may land before this rank is set up
@@ -308,7 +309,7 @@ class _RK4:
         if ng > 0:
             off = self.nupd * self.dtype.itemsize
             check(fn("fus_fill", self.dtype)(0.0, self.b.data_ptr() + off, ng, current_stream()), "fus_fill")
-            if self.westervelt:
+            if self._m_accum:
                 check(fn("fus_fill", self.dtype)(0.0, self.m.data_ptr() + off, ng, current_stream()), "fus_fill")
 
     def _assemble(self, stage, g, dg, use_table, x, vn):  # pragma: no cover - abstract
@@ -323,7 +324,7 @@ class _RK4:
 
     def _halo_reverse(self):
         if self.halo is not None:
-            if self.westervelt:
+            if self._m_accum:
                 self.halo.reverse(self.b, self.m)
             else:
                 self.halo.reverse(self.b)
@@ -554,6 +555,13 @@ class WesterveltSpectral3D(_RK4):
     facets with ``facet_coeff1_1 = 1/rho`` (g) and ``facet_coeff2_1 = delta/(rho c^2)``
     (dg/dt); absorbing facets with ``facet_coeff1_2 = delta/(rho c^3)`` (into m0)
     and ``facet_coeff2_2 = -1/(rho c)``.
+
+    ``mass_form="pointwise"`` (default): the lumped mass is diagonal, so the two cell-mass
+    applications of every stage (:609-612 ``m += M(c2; un)``, :626-628 ``b += M(c5; vn^2)``)
+    equal ``un * m2`` and ``vn^2 * m5`` with ``m2 = M(c2; 1)``, ``m5 = M(c5; 1)`` assembled
+    once: they move into the close kernel, the stage kernel is the dual stiffness action
+    alone and only ``b`` is reverse-exchanged.  ``mass_form="cells"`` recomputes them over
+    the cells every stage as the reference does (one pass over G, detJ and the dofmap).
     """
 
     westervelt = True
@@ -562,10 +570,15 @@ class WesterveltSpectral3D(_RK4):
                  cell_coeff3, cell_coeff4, cell_coeff5, bfacet_dofmap1=None, detJ_f1=None,
                  facet_coeff1_1=None, facet_coeff2_1=None, bfacet_dofmap2=None, detJ_f2=None,
                  facet_coeff1_2=None, facet_coeff2_2=None, halo=None, source=None,
-                 source_at_stage_time=True, use_graph=True, geometry="stream", weights=None):
+                 source_at_stage_time=True, use_graph=True, geometry="stream", weights=None,
+                 mass_form="pointwise"):
         super().__init__(P, float_type, ndofs, dofmap, G, dphi_1D, halo, source,
                          source_at_stage_time, use_graph, geometry, weights)
         torch = _torch()
+        if mass_form not in ("pointwise", "cells"):
+            raise ValueError("mass_form must be 'pointwise' or 'cells'")
+        self.mass_form = mass_form
+        self._m_accum = mass_form == "cells"
         self.detJ = _dev(detJ, self.T)
         self.c2, self.c3 = _dev(cell_coeff2, self.T), _dev(cell_coeff3, self.T)
         self.c4, self.c5 = _dev(cell_coeff4, self.T), _dev(cell_coeff5, self.T)
@@ -589,8 +602,18 @@ class WesterveltSpectral3D(_RK4):
         if bd2.shape[0]:
             terms.append(("absb", bd2, _dev(detJ_f2, self.T), _dev(facet_coeff2_2, self.T)))
         self._boundary_setup(terms)
-        self.m.zero_()  # state-dependent part, accumulated per stage, zeroed by the close kernel
-        self._setup_geometry(self.detJ, ["c2", "c3", "c4", "c5"])
+        self.m.zero_()  # "cells" form: state-dependent part, accumulated per stage, zeroed by the close kernel
+        self.m2 = self.m5 = None
+        if not self._m_accum:
+            # lumped M(c2; 1) and M(c5; 1), owner-complete like m0
+            self.m2, self.m5 = self._zx(), self._zx()
+            self._mass(ones, self.c2, self.m2, self.detJ, self.dofmap)
+            self._mass(ones, self.c5, self.m5, self.detJ, self.dofmap)
+            if self.halo is not None:
+                self.halo.reverse(self.m2, self.m5)
+        self._setup_geometry(self.detJ if self._m_accum else None, ["c2", "c3", "c4", "c5"])
+        if not self._m_accum:
+            self.detJ = None  # only the set-up needed it
 
     def _state(self):
         return super()._state() + [self.m0]
@@ -606,6 +629,24 @@ class WesterveltSpectral3D(_RK4):
         x = self.un if x is None else x
         vn = self.ku if vn is None else vn
         nr, na, nc, st = self.nrect, self.naff, self.ncells, current_stream()
+        if not self._m_accum:
+            # b += K(c3; un) + K(c4; vn): the dual stiffness action, one pass over G
+            if nr:
+                check(fn("fus_stiffness2_rect", self.dtype)(
+                    x.data_ptr(), self.c3.data_ptr(), vn.data_ptr(), self.c4.data_ptr(), self.b.data_ptr(),
+                    self.Gc.data_ptr(), self.dofmap.data_ptr(), None, nr, self.P, FUS_TABLES_RESIDENT, st),
+                    "fus_stiffness2_rect")
+            if na > nr:
+                check(fn("fus_stiffness2_affine", self.dtype)(
+                    x.data_ptr(), self.c3[nr:].data_ptr(), vn.data_ptr(), self.c4[nr:].data_ptr(), self.b.data_ptr(),
+                    self.Gc[nr:].data_ptr(), self._weights.data_ptr(), self.dofmap[nr:].data_ptr(), None, na - nr,
+                    self.P, FUS_TABLES_RESIDENT, st), "fus_stiffness2_affine")
+            if na < nc:
+                check(fn("fus_stiffness2", self.dtype)(
+                    x.data_ptr(), self.c3[na:].data_ptr(), vn.data_ptr(), self.c4[na:].data_ptr(), self.b.data_ptr(),
+                    self.G.data_ptr(), self.dofmap[na:].data_ptr(), None, nc - na, self.P, FUS_TABLES_RESIDENT, st),
+                    "fus_stiffness2")
+            return
         if nr:
             check(fn("fus_stiffness_westervelt_rect", self.dtype)(
                 x.data_ptr(), self.c3.data_ptr(), vn.data_ptr(), self.c4.data_ptr(),
@@ -628,6 +669,12 @@ class WesterveltSpectral3D(_RK4):
 
     def _close(self, stage, dt, count_step, base, acc):
         u, v, u0, v0, bdt, adt, mode = self._close_args(stage, dt, base, acc)
+        if not self._m_accum:
+            check(fn("fus_rk_close_westervelt_pw", self.dtype)(
+                u, v, u0, v0, self.ku.data_ptr(), None, self.un.data_ptr(), self.b.data_ptr(), self.m0.data_ptr(),
+                self.m2.data_ptr(), self.m5.data_ptr(), bdt, adt, mode, self.nupd,
+                self.step_dev.data_ptr() if count_step else None, current_stream()), "fus_rk_close_westervelt_pw")
+            return
         check(fn("fus_rk_close_westervelt", self.dtype)(
             u, v, u0, v0, self.ku.data_ptr(), None, self.un.data_ptr(), self.b.data_ptr(), self.m.data_ptr(),
             self.m0.data_ptr(), bdt, adt, mode, self.nupd, self.step_dev.data_ptr() if count_step else None,
@@ -636,4 +683,7 @@ class WesterveltSpectral3D(_RK4):
     def stage_bytes(self):
         s = self.dtype.itemsize
         Nd = self.n**3
-        return super().stage_bytes() + (self.ncells - self.naff) * Nd * s + 6 * s * self.ndofs
+        if self._m_accum:  # + detJ stream, second gather, m read-modify-write, m0, m zero
+            return super().stage_bytes() + (self.ncells - self.naff) * Nd * s + 6 * s * self.ndofs
+        # pointwise: + second gather (vn) in the stage kernel; close passes 11 + 15 + 15 + 11 per step
+        return super().stage_bytes() + s * self.ndofs + (13 - 10.25) * s * self.ndofs

@@ -155,6 +155,20 @@ int fus_stiffness_westervelt_rect_f32(const float* un, const float* c3, const fl
                                       const int32_t* dofmap, const float* dphi, int64_t ncells, int P,
                                       int flags, void* stream);
 
+/* y += K(ca; xa) + K(cb; xb) on affine / rectilinear cells (fus_stiffness2_* with compressed geometry). */
+int fus_stiffness2_affine_f64(const double* xa, const double* ca, const double* xb, const double* cb,
+                              double* y, const double* Gc, const double* wq, const int32_t* dofmap,
+                              const double* dphi, int64_t ncells, int P, int flags, void* stream);
+int fus_stiffness2_affine_f32(const float* xa, const float* ca, const float* xb, const float* cb,
+                              float* y, const float* Gc, const float* wq, const int32_t* dofmap,
+                              const float* dphi, int64_t ncells, int P, int flags, void* stream);
+int fus_stiffness2_rect_f64(const double* xa, const double* ca, const double* xb, const double* cb,
+                            double* y, const double* Gc, const int32_t* dofmap, const double* dphi,
+                            int64_t ncells, int P, int flags, void* stream);
+int fus_stiffness2_rect_f32(const float* xa, const float* ca, const float* xb, const float* cb,
+                            float* y, const float* Gc, const int32_t* dofmap, const float* dphi,
+                            int64_t ncells, int P, int flags, void* stream);
+
 /* Per cell: Gc[c,:] = mean_q G[c,q,:] / wq[q], detJc[c] = mean_q detJ[c,q] / wq[q] (detJ may be
  * NULL) and affine[c] = 1 when every G[c,q,:] / wq[q] (and detJ[c,q] / wq[q]) lies within
  * tol * max|Gc[c,:]| (tol * |detJc[c]|) of that mean, else 0.  One CTA per cell. */
@@ -316,6 +330,22 @@ int fus_rk_close_westervelt_f32(float* u, float* v, float* u0, float* v0, float*
                                 float* un, float* b, float* m, const float* m0, float bdt,
                                 float adt_next, int next_mode, int64_t n, int64_t* step_dev,
                                 void* stream);
+
+/* Pointwise form of the Westervelt stage closing.  The lumped mass is diagonal, so the cell-mass
+ * pair of cuda/demo_nonlinear_bowl.py:609-612, 626-628 needs no pass over the cells:
+ *   M(c2; un) = un * m2,  M(c5; vn^2) = vn^2 * m5   with m2 = M(c2; 1), m5 = M(c5; 1) assembled once.
+ *   kv = (b + vn^2 m5) / (m0 + un m2) ; u += bdt*ku ; v += bdt*kv ; then as fus_rk_close
+ * (un, vn = ku: the stage input; in next_mode 3 they are u0, v0).  The stage kernel is then
+ * fus_stiffness2_* (both stiffness terms, one pass over G) and only b is reverse-exchanged. */
+int fus_rk_close_westervelt_pw_f64(double* u, double* v, double* u0, double* v0, double* ku,
+                                   double* kv, double* un, double* b, const double* m0,
+                                   const double* m2, const double* m5, double bdt,
+                                   double adt_next, int next_mode, int64_t n, int64_t* step_dev,
+                                   void* stream);
+int fus_rk_close_westervelt_pw_f32(float* u, float* v, float* u0, float* v0, float* ku, float* kv,
+                                   float* un, float* b, const float* m0, const float* m2,
+                                   const float* m5, float bdt, float adt_next, int next_mode,
+                                   int64_t n, int64_t* step_dev, void* stream);
 
 /* --------------------------------------------------------------------- *
  * Geometry precompute on the device - cuda/precompute.py:17-163
