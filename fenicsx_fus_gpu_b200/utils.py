@@ -212,6 +212,15 @@ def colour_order(colours):
     return perm, np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
 
 
+def compute_eval_params(mesh, points, float_type):
+    """``(points_on_proc, cells)`` of cuda/utils.py:117-154 - implemented in ``sampling.py``
+    (bin grid + Newton pull-back instead of DOLFINx bounding-box trees); re-exported here because the
+    reference's piston / bowl demos import it from ``utils``."""
+    from .sampling import compute_eval_params as _impl
+
+    return _impl(mesh, points, float_type)
+
+
 def compute_diffusivity_of_sound(w0: float, c0: float, alpha: float) -> float:
     """``delta = 2 alpha c0^3 / w0^2`` with alpha in dB/m converted to Np/m -
     cuda/utils.py:157-162."""

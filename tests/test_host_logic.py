@@ -283,3 +283,36 @@ def test_compute_eval_params_and_interpolation_known_answers():
     e, c = sp.compute_eval_params(box, np.array([[5.0], [5.0], [5.0]]), np.float32)
     assert e.shape == (0, 3) and e.dtype == np.float32 and c == []
     assert sp.compute_eval_params(box, np.zeros((3, 0)), np.float64)[1] == []
+
+
+def test_shim_modules_export_every_name_the_reference_scripts_import():
+    """shim/{operators,scatterer,precompute,utils}.py first on sys.path: the bare-name imports of the
+    reference's cuda/ scripts (demo_linear_box.py:21-38, demo_linear_piston.py, demo_nonlinear_bowl.py,
+    time_operators.py, test_operators.py, test_scatterer.py) resolve to this package."""
+    import importlib
+    import os
+    import sys
+
+    shim = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "shim")
+    wanted = {
+        "operators": ["mass_operator", "stiffness_operator", "axpy", "copy", "fill", "pointwise_divide", "square"],
+        "scatterer": ["scatter_forward", "scatter_reverse", "pack_fwd", "unpack_fwd", "pack_rev", "unpack_rev"],
+        "precompute": ["compute_scaled_jacobian_determinant", "compute_scaled_geometrical_factor",
+                       "compute_boundary_facets_scaled_jacobian_determinant"],
+        "utils": ["compute_scatterer_data", "facet_integration_domain", "compute_eval_params",
+                  "compute_diffusivity_of_sound"],
+    }
+    saved = {m: sys.modules.pop(m, None) for m in wanted}
+    sys.path.insert(0, shim)
+    try:
+        for mod, names in wanted.items():
+            m = importlib.import_module(mod)
+            assert os.path.dirname(os.path.abspath(m.__file__)) == shim
+            for n in names:
+                assert hasattr(m, n), f"{mod}.{n}"
+    finally:
+        sys.path.remove(shim)
+        for mod in wanted:
+            sys.modules.pop(mod, None)
+            if saved[mod] is not None:
+                sys.modules[mod] = saved[mod]
