@@ -126,6 +126,7 @@ def setup_from_dolfinx(mesh, V, basis_degree, float_type=np.float64, comm=None, 
     pre.compute_geometry(dev["G"], dev["detJ"], (dev["x_dofs"], dev["x_g"]), num_cells, dev["dphi"], dev["wts"])
     # smallest cell diameter of this rank (cpp.mesh.h, cuda/demo_linear_box.py:103-108): longest vertex distance
     cc = x_g[x_dofs].astype(np.float64)
-    h = float(np.sqrt(((cc[:, :, None, :] - cc[:, None, :, :]) ** 2).sum(-1)).max(axis=(1, 2)).min()) if num_cells else 0.0
+    h = float(np.sqrt(((cc[:, :, None, :] - cc[:, None, :, :]) ** 2).sum(-1)).max(axis=(1, 2)).min()) if num_cells else np.inf
+    h = utils.global_min(h, comm)  # mesh_size of the reference: the minimum over all ranks
     return Setup(int(basis_degree), float_type, rank, world, HostMesh(x_dofs, x_g), tables, dofmap, nlocal + nghost,
                  nlocal, int(imap.size_global), (num_cells,), halo, dev, h)

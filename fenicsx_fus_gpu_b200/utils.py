@@ -212,6 +212,21 @@ def colour_order(colours):
     return perm, np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
 
 
+def global_min(value: float, comm=None) -> float:
+    """Minimum of ``value`` over the ranks - the ``comm.Allreduce(hmin, mesh_size, op=MPI.MIN)``
+    of cuda/demo_linear_box.py:103-108 over ``torch.distributed`` (gloo: CPU tensor; nccl: staged
+    through the device).  Without an initialised process group it is the value itself."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(comm) == 1:
+        return float(value)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(comm) == "nccl" else torch.device("cpu")
+    t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=comm)
+    return float(t.item())
+
+
 def compute_eval_params(mesh, points, float_type):
     """``(points_on_proc, cells)`` of cuda/utils.py:117-154 - implemented in ``sampling.py``
     (bin grid + Newton pull-back instead of DOLFINx bounding-box trees); re-exported here because the

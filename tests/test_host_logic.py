@@ -116,6 +116,8 @@ def _gloo_worker(rank, world, port, golden_dir, q):
         for rb, ix in zip(recv, gd[0]):
             orc.unpack_rev(rb.numpy(), rv, np.ascontiguousarray(ix, np.int64))
         ok &= bool(np.allclose(rv, g[f"r{rank}_rev"], rtol=1e-15, atol=0))
+        # mesh_size = min over ranks of the local hmin (cuda/demo_linear_box.py:103-108)
+        ok &= utils.global_min(0.5 + rank) == 0.5 and utils.global_min(2.0 - rank) == 1.0
         q.put((rank, ok))
     finally:
         dist.destroy_process_group()
@@ -204,6 +206,10 @@ def test_facet_integration_domain_matches_box_facets():
         fids = np.array([c2f[c, l] for c, l in want], np.int32)
         got = utils.facet_integration_domain(fids, M())
         assert np.array_equal(got, want)
+
+
+def test_global_min_without_process_group():
+    assert utils.global_min(0.25) == 0.25
 
 
 def test_diffusivity_of_sound():
