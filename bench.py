@@ -13,12 +13,22 @@ block-partitioned, every GPU keeps an 80^3 block (weak scaling) and the ghost
 dofs are exchanged over NCCL each stage.
 
 The JSON line: ``value`` = fused-RK-stage throughput in GDoF/s (global dofs x 4
-stages x K / time), the metric BASELINE.json names ("operator GDoF/s and RK
-time-steps/s"); ``steps_per_s`` and the stand-alone operator GDoF/s ride along.
-``roofline`` is the stiffness kernel (the dominant kernel) against the measured
-HBM peak; ``cpu_baseline`` is the reference's CPU path (its own C++
-sum-factorisation templates when oracle/_ref is built, else the C port) timed on
-this host's cores on a bounded sample of the same workload.
+stages x K / time, K graph-replayed steps, state resident in HBM), the metric
+BASELINE.json names ("operator GDoF/s and RK time-steps/s"); ``steps_per_s`` and the
+stand-alone operator GDoF/s ride along.  ``e2e`` = the same steps with, per step, the
+H2D copy of the step's source amplitudes from pinned memory and the D2H read of a
+sampled pressure plane; ``e2e_operator_host_buffers`` = one stiffness action through
+the C ABI with x and y in pinned HOST memory.  ``roofline`` = the dominant kernel (the
+stiffness kernel; the dual-stiffness stage kernel for the Westervelt workload):
+algorithmic bytes / its mean duration inside the RK steps (CUDA events
+around each launch), against the measured HBM peak, with the stand-alone back-to-back
+figure beside it.  ``stage_roofline`` = the whole fused stage on the bytes it moves.
+``affine_geometry`` = the same steps with ``geometry="auto"`` (cells with a constant
+Jacobian keep 6 geometric factors; extra, not the headline; ``--geometry auto`` makes it
+the measured path and says so in ``config``).  ``cpu_baseline`` is the reference's CPU
+path (its own C++ sum-factorisation templates when oracle/_ref is built, else the C
+port) timed on this host's cores on a bounded sample of the same workload.
+``--workload linear_piston|nonlinear_bowl`` time BASELINE.json's other demo configs.
 """
 
 from __future__ import annotations
