@@ -322,3 +322,50 @@ def test_shim_modules_export_every_name_the_reference_scripts_import():
             sys.modules.pop(mod, None)
             if saved[mod] is not None:
                 sys.modules[mod] = saved[mod]
+
+
+def test_eval_params_keep_only_the_points_of_this_rank():
+    """compute_eval_params on the parts of a partitioned box: every interior point is found by exactly
+    the ranks whose cells contain it (shared faces: both), as `points_on_proc` of cuda/utils.py:139-150."""
+    from fenicsx_fus_gpu_b200 import sampling as sp
+
+    parts = S.partition_box((4, 4, 4), 2, 8, lengths=(1.0, 1.0, 1.0))
+    rng = np.random.default_rng(2)
+    pts = rng.uniform(0.01, 0.99, (200, 3))
+    pts = pts[np.all(np.abs(pts - 0.5) > 1e-3, axis=1)]  # keep clear of the rank interfaces
+    count = np.zeros(pts.shape[0], int)
+    for p in parts:
+        xp, cells = sp.compute_eval_params(p.mesh, pts.T, np.float64)
+        assert len(cells) == xp.shape[0] and all(0 <= c < p.mesh.num_cells for c in cells)
+        lo = np.array(p.mesh.cell_origin) / 4.0
+        hi = lo + np.array(p.mesh.ncells) / 4.0
+        inside = np.all((pts > lo) & (pts < hi), axis=1)
+        assert np.array_equal(xp, pts[inside])
+        count += inside
+    assert np.all(count == 1)
+
+
+def test_partition_properties_on_random_grids():
+    """Random cell counts / rank grids: owned ranges tile the global numbering, every dof has one
+    owner, ghost owners really own their dofs, dest-rank lists mirror the ghost lists."""
+    rng = np.random.default_rng(11)
+    for _ in range(6):
+        grid = tuple(int(v) for v in rng.integers(1, 4, 3))
+        ncells = tuple(int(g * rng.integers(1, 3) + rng.integers(0, 2)) for g in grid)
+        P = int(rng.integers(1, 4))
+        R = grid[0] * grid[1] * grid[2]
+        parts = S.partition_box(ncells, P, R, grid=grid)
+        ranges = [p.index_map.local_range for p in parts]
+        assert ranges[0][0] == 0 and ranges[-1][1] == parts[0].index_map.size_global == S.num_dofs(ncells, P)
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        ghosted_by = {}
+        for p in parts:
+            im = p.index_map
+            for g, o in zip(im.ghosts, im.owners):
+                assert ranges[o][0] <= g < ranges[o][1] and o != p.rank
+                ghosted_by.setdefault((int(o), int(g) - ranges[o][0]), set()).add(p.rank)
+            assert p.dofmap.min() >= 0 and p.dofmap.max() == im.size_local + im.num_ghosts - 1
+        for p in parts:
+            dest = p.index_map.index_to_dest_ranks()
+            for i in range(p.index_map.size_local):
+                assert set(int(r) for r in dest.links(i)) == ghosted_by.get((p.rank, i), set())
