@@ -52,7 +52,6 @@ F0, P0, C0, RHO = 0.5e6, 60000.0, 1500.0, 1000.0
 DOMAIN_LENGTH = 0.12
 N_PER_GPU = 80  # int(2 * 0.12 / (1500 / 0.5e6)) = 80 cells per direction
 CFL = 0.65
-CPU_SAMPLE_N = 24  # cells per direction of the bounded CPU sample (P=4: 912 673 dofs)
 
 
 def peaks():
@@ -78,17 +77,23 @@ class Clocks:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, gpu_id):
+        """``gpu_id``: anything ``nvidia-smi --id`` takes - the GPU's UUID (robust under torchrun,
+        whatever CUDA_VISIBLE_DEVICES says) or its index."""
+        self.index, self.proc, self.lines = gpu_id, None, []
 
-    def start(self):
+    def start(self, wait_first=8.0):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
+            return
+        t0 = time.time()
+        while not self.lines and time.time() - t0 < wait_first:  # the first sample can take seconds on a busy 8-GPU box
+            time.sleep(0.05)
 
     def _pump(self):
         for ln in self.proc.stdout:
@@ -97,9 +102,9 @@ class Clocks:
     def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
-        rows = [ln for ts, ln in self.lines if t0 - 0.05 <= ts <= t1 + 0.15] or [ln for _, ln in self.lines]
+        rows = [ln for ts, ln in self.lines if t0 <= ts <= t1 + 0.05] or [ln for _, ln in self.lines]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in rows:
@@ -135,7 +140,8 @@ WORKLOADS = {
 }
 
 
-def build_problem(rank, world, n_per_gpu, dtype, halo_kind, workload="linear_box", degree=None, geometry="stream"):
+def build_problem(rank, world, n_per_gpu, dtype, halo_kind, workload="linear_box", degree=None, geometry="stream",
+                  split_cells=True):
     """The demo's preamble through fenicsx_fus_gpu_b200.problem (device geometry,
     block partition, halo).  Returns the solver and an info dict."""
     from fenicsx_fus_gpu_b200 import problem
@@ -160,17 +166,18 @@ def build_problem(rank, world, n_per_gpu, dtype, halo_kind, workload="linear_box
     def make_solver(geometry="stream"):
         if workload == "linear_box":
             return problem.linear_solver(su, source_facets=[2], absorbing_facets=[3], rho=W["rho"], c0=W["c0"],
-                                         f0=W["f0"], p0=P0, geometry=geometry)
+                                         f0=W["f0"], p0=P0, geometry=geometry, split_cells=split_cells)
         if workload == "linear_piston":
             piston = problem.disc(0, 1, (0.5 * lengths[0], 0.5 * lengths[1]), 0.01)
             return problem.linear_solver(
                 su, source_facets=[0], absorbing_facets=[0, 1, 2, 3, 4, 5], rho=W["rho"], c0=W["c0"], f0=W["f0"],
-                p0=P0, source_predicate=piston, geometry=geometry,
+                p0=P0, source_predicate=piston, geometry=geometry, split_cells=split_cells,
                 absorbing_predicate=lambda cen: ~(piston(cen) & (cen[:, 2] < 0.5 * h)))
         centre = (0.5 * lengths[1], 0.5 * lengths[2])
         return problem.westervelt_solver(
             su, source_facets=[2], absorbing_facets=[0, 1, 2, 3, 4, 5], rho=W["rho"], c0=W["c0"], f0=W["f0"],
-            beta=3.5, alpha_dB=0.2, source_predicate=problem.disc(1, 2, centre, 0.3 * lengths[1]), geometry=geometry)
+            beta=3.5, alpha_dB=0.2, source_predicate=problem.disc(1, 2, centre, 0.3 * lengths[1]), geometry=geometry,
+            split_cells=split_cells)
 
     solver = make_solver(geometry)
     info = dict(make_solver=make_solver, ncells_local=su.mesh.num_cells, ndofs_local=su.ndofs, nlocal=su.nlocal, global_cells=ncells,
@@ -181,114 +188,93 @@ def build_problem(rank, world, n_per_gpu, dtype, halo_kind, workload="linear_box
 
 
 # --------------------------------------------------------------------------- #
-# CPU arm: the reference's CPU path on a bounded sample
+# baseline arms: the reference's own code on this box
 # --------------------------------------------------------------------------- #
 
 
-class CpuRK:
-    """numba-cpu/demo_linear_box.py:425-459 with the reference operators
-    (oracle/_ref C++ templates, else the oracle C port), ``cores`` threads each
-    owning 1/k of the cells - the reference scales through MPI ranks only."""
+def time_cpu(steps, warmup, n, degree, dtype, kind=None):
+    """The reference's CPU path (baseline/cpu_arm.py): the WHOLE n^3-cell box of the workload,
+    split over one process per host core, stepped ``steps`` times with the reference's own
+    numba-cpu operators (``kind`` "cpp": its C++ templates; "port": the oracle C port)."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import cpu_arm
 
-    def __init__(self, n, dtype, cores):
-        from fenicsx_fus_gpu_b200 import substrate as S
-        from oracle import oracle as orc
-
-        self.orc, self.cores, self.dtype = orc, cores, dtype
-        self.kind = "reference" if orc.ref_lib() is not None else "port"
-        tb = S.element_tables(P, "basix", dtype)
-        h = DOMAIN_LENGTH / N_PER_GPU
-        mesh = S.create_box(n, h * n, dtype=dtype)
-        self.dofmap = S.tensor_dofmap(mesh, P)
-        self.nd = S.num_dofs(n, P)
-        nc = mesh.num_cells
-        self.G = np.zeros((nc, tb.n**3, 6), dtype)
-        detJ = np.zeros((nc, tb.n**3), dtype)
-        orc.compute_scaled_geometrical_factor(self.G, (mesh.x_dofs, mesh.x_g), nc, tb.dphi, tb.wts)
-        orc.compute_scaled_jacobian_determinant(detJ, (mesh.x_dofs, mesh.x_g), nc, tb.dphi, tb.wts)
-        self.c2 = np.full(nc, -1.0 / RHO, dtype)
-        self.m = np.zeros(self.nd, dtype)
-        orc.mass_operator(np.ones(self.nd, dtype), np.full(nc, 1.0 / RHO / C0 / C0, dtype), self.m, detJ, self.dofmap)
-        bd1, bd2 = S.boundary_facets(mesh, 2), S.boundary_facets(mesh, 3)
-        self.fd1 = S.facet_dofmap(self.dofmap, bd1, tb.local_facet_dof)
-        self.fd2 = S.facet_dofmap(self.dofmap, bd2, tb.local_facet_dof)
-        self.dJ1 = np.zeros((bd1.shape[0], tb.n**2), dtype)
-        self.dJ2 = np.zeros((bd2.shape[0], tb.n**2), dtype)
-        orc.compute_boundary_facets_scaled_jacobian_determinant(self.dJ1, (mesh.x_dofs, mesh.x_g), bd1, tb.dphi_f, tb.wts_f)
-        orc.compute_boundary_facets_scaled_jacobian_determinant(self.dJ2, (mesh.x_dofs, mesh.x_g), bd2, tb.dphi_f, tb.wts_f)
-        self.fc1 = np.full(bd1.shape[0], 1.0 / RHO, dtype)
-        self.fc2 = np.full(bd2.shape[0], -1.0 / RHO / C0, dtype)
-        self.dphi = tb.dphi_1D
-        self.dt = cfl_dt(h)
-        z = lambda: np.zeros(self.nd, dtype)  # noqa: E731
-        self.u, self.v, self.u0, self.v0, self.un, self.vn = z(), z(), z(), z(), z(), z()
-        self.ku, self.kv, self.g, self.b = z(), z(), z(), z()
-        self.ybuf = np.zeros((cores, self.nd), dtype)
-        self.t = 0.0
-        self.sample = f"{n}^3 cells, degree {P}, {self.nd} dofs, {np.dtype(dtype).name}"
-
-    def step(self):
-        from fenicsx_fus_gpu_b200.solver import A_RUNGE, B_RUNGE, C_RUNGE, linear_source
-
-        o, dt = self.orc, self.dt
-        self.u0[:] = self.u
-        self.v0[:] = self.v
-        for i in range(4):
-            self.un[:] = self.u0
-            self.vn[:] = self.v0
-            o.axpy(A_RUNGE[i] * dt, self.ku, self.un)
-            o.axpy(A_RUNGE[i] * dt, self.kv, self.vn)
-            o.copy(self.vn, self.ku)
-            o.fill(linear_source(self.t + C_RUNGE[i] * dt, F0, P0, C0)[0], self.g)
-            o.fill(0.0, self.b)
-            self.ybuf[:] = 0
-            o.stiffness_ranks(P, self.un, self.c2, self.ybuf, self.G, self.dofmap, self.dphi, self.cores)
-            self.b += self.ybuf.sum(axis=0)
-            o.mass_operator(self.g, self.fc1, self.b, self.dJ1, self.fd1)
-            o.mass_operator(self.vn, self.fc2, self.b, self.dJ2, self.fd2)
-            o.pointwise_divide(self.b, self.m, self.kv)
-            o.axpy(B_RUNGE[i] * dt, self.ku, self.u)
-            o.axpy(B_RUNGE[i] * dt, self.kv, self.v)
-        self.t += dt
+    return cpu_arm.run(n=n, P=degree, dtype="float64" if dtype == "f64" else "float32", steps=steps,
+                       warmup=warmup, kind=kind)
 
 
-def time_cpu(steps, warmup, budget_s=15.0):
-    """``cores`` threads, each stepping its own box of 1/cores of the sample
-    (the reference kernels are serial per MPI rank; this is ``mpirun -n cores``
-    on this host without the halo cost).  Runs ``steps`` RK4 steps, extended
-    until about ``budget_s`` seconds of work have been timed."""
-    cores = len(os.sched_getaffinity(0))
-    n = max(4, int(round(CPU_SAMPLE_N / cores ** (1.0 / 3.0))))
-    rks = [CpuRK(n, np.float64, 1) for _ in range(cores)]
-    done = [0] * cores
-    t_end = [0.0] * cores
-    go = threading.Barrier(cores + 1)
+def reference_cuda_arm(n, degree, dtype, reps=10):
+    """The reference's own Numba-CUDA kernels (cuda/operators.py:18-192, shipped unmodified as
+    baseline/_ref/cuda/operators.py) on THIS GPU, launched with the reference's launch shapes and
+    timed with its protocol (cuda/time_operators.py:204-222, 272-290: one warm-up, 10 launches each
+    bracketed by perf_counter_ns + cuda.synchronize), beside this repo's kernels on the same arrays
+    with the same protocol.  If Numba cannot JIT for this GPU the error text is the result."""
+    import torch
 
-    def body(i):
-        rk = rks[i]
-        for _ in range(max(1, warmup)):
-            rk.step()
-        go.wait()
-        t0 = time.perf_counter()
-        while done[i] < steps or time.perf_counter() - t0 < budget_s:
-            rk.step()
-            done[i] += 1
-            if time.perf_counter() - t0 > 2.0 * budget_s:
-                break
-        t_end[i] = time.perf_counter()
+    from fenicsx_fus_gpu_b200 import operators as ops
+    from fenicsx_fus_gpu_b200 import problem
 
-    th = [threading.Thread(target=body, args=(i,)) for i in range(cores)]
-    [t.start() for t in th]
-    go.wait()
-    t0 = time.perf_counter()
-    [t.join() for t in th]
-    el = max(t_end) - t0
-    work = sum(rk.nd * 4 * d for rk, d in zip(rks, done))
-    nsteps = min(done)
-    return dict(value=work / el / 1e9, unit="GDoF/s", cores=cores, kind=rks[0].kind,
-                sample=f"{cores} threads x {nsteps}+ RK4 steps, each thread its own {rks[0].sample} box "
-                       f"(mpirun -n {cores} emulation without halo cost), {el:.1f} s",
-                ms_per_step=el / max(1, nsteps) * 1e3, steps_per_s=nsteps / el, steps=nsteps)
+    np_t = np.float64 if dtype == "f64" else np.float32
+    su = problem.box_setup(degree, n, 0.12 / 80 * n, np_t)
+    nc, nd, nn = su.mesh.num_cells, su.ndofs, degree + 1
+    G, detJ, dm = su.dev["G"], su.dev["detJ"], su.dev["dofmap"]
+    D = torch.from_numpy(su.tables.dphi_1D).cuda()
+    c = torch.ones(nc, dtype=G.dtype, device="cuda")
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(nd, dtype=G.dtype, device="cuda", generator=gen)
+    y = torch.zeros(nd, dtype=G.dtype, device="cuda")
+    out = {"workload": f"mass + stiffness action, degree {degree}, {n}^3 cells, {nd} dofs, {dtype}",
+           "protocol": "1 warm-up + 10 launches, perf_counter_ns around launch + device synchronise, "
+                       "output zero-filled outside the timed region (cuda/time_operators.py:204-222, 272-290)"}
+
+    def timed(launch):
+        y.zero_()
+        launch()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            y.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter_ns()
+            launch()
+            torch.cuda.synchronize()
+            ts.append((time.perf_counter_ns() - t0) * 1e-9)
+        return float(np.mean(ts)), float(np.min(ts))
+
+    K = ops.stiffness_operator(degree, np_t)
+    t_k, t_k_min = timed(lambda: K[nc, (nn, nn, nn)](x, c, y, G, dm, D))
+    y_ours = y.clone()
+    t_m, t_m_min = timed(lambda: ops.mass_operator[1, 128](x, c, y, detJ, dm))
+    m_ours = y.clone()
+    out["ours"] = {"stiffness_gdofs": nd / t_k / 1e9, "stiffness_ms": t_k * 1e3, "stiffness_ms_min": t_k_min * 1e3,
+                   "mass_gdofs": nd / t_m / 1e9, "mass_ms": t_m * 1e3, "mass_ms_min": t_m_min * 1e3}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref", "cuda"))
+        import numba.cuda as ncuda
+
+        if "operators" in sys.modules:
+            del sys.modules["operators"]
+        import operators as ref_ops  # the reference's cuda/operators.py, unmodified
+
+        ncuda.select_device(torch.cuda.current_device())
+        arr = lambda t: ncuda.as_cuda_array(t)  # noqa: E731  zero-copy views of the same device arrays
+        xd, yd, cd, Gd, Jd, dmd, Dd = (arr(t) for t in (x, y, c, G, detJ, dm, D))
+        stiff = ref_ops.stiffness_operator(degree, np_t)
+        t_k, t_k_min = timed(lambda: stiff[nc, (nn, nn, nn)](xd, cd, yd, Gd, dmd, Dd))
+        e_k = float((y - y_ours).norm() / y_ours.norm())
+        nb = (dm.numel() + 127) // 128
+        t_m, t_m_min = timed(lambda: ref_ops.mass_operator[nb, 128](xd, cd, yd, Jd, dmd))
+        e_m = float((y - m_ours).norm() / m_ours.norm())
+        out["reference_numba_cuda"] = {
+            "stiffness_gdofs": nd / t_k / 1e9, "stiffness_ms": t_k * 1e3, "stiffness_ms_min": t_k_min * 1e3,
+            "mass_gdofs": nd / t_m / 1e9, "mass_ms": t_m * 1e3, "mass_ms_min": t_m_min * 1e3,
+            "launch": f"stiffness[{nc}, ({nn},{nn},{nn})], mass[{nb}, 128]",
+            "rel_l2_ours_vs_reference": {"stiffness": e_k, "mass": e_m}}
+        out["speedup"] = {"stiffness": out["ours"]["stiffness_gdofs"] / out["reference_numba_cuda"]["stiffness_gdofs"],
+                          "mass": out["ours"]["mass_gdofs"] / out["reference_numba_cuda"]["mass_gdofs"]}
+    except Exception as e:  # Numba cannot drive this GPU / toolkit: the error text is the record
+        out["reference_numba_cuda"] = {"unavailable": f"{type(e).__name__}: {e}"[:600]}
+    return out
 
 
 # --------------------------------------------------------------------------- #
@@ -301,7 +287,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--n-per-gpu", type=int, default=0, help="cells per direction per GPU (default: the workload's)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--workload", default="linear_box", choices=sorted(WORKLOADS),
@@ -309,12 +295,16 @@ def main():
     ap.add_argument("--degree", type=int, default=0, help="override the workload's polynomial degree (2..7)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-affine", action="store_true", help="skip the extra affine-geometry measurement")
+    ap.add_argument("--no-extras", action="store_true", help="only the timed region + roofline (sweeps)")
     ap.add_argument("--geometry", default="stream", choices=["stream", "auto"],
                     help="stream (default, the reference's data flow: G read in full every stage) or auto "
                          "(cells with a constant Jacobian keep 6 factors; the JSON line says so in config)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU halo: fused put/get kernels over NVLink peer memory, or NCCL send/recv")
+    ap.add_argument("--no-split", action="store_true", help="p2p halo without the interior/interface cell split (A/B)")
     ap.add_argument("--no-graph", action="store_true", help="launch the steps eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--cpu-kind", default=None, choices=["numba", "cpp", "port"], help="CPU arm implementation")
+    ap.add_argument("--sustain-steps", type=int, default=250, help="steps of the extra >= 1 s sustained measurement")
     ap.add_argument("--watchdog", type=int, default=0, help="dump all Python stacks to stderr after this many seconds")
     ap.add_argument("-v", "--verbose", action="store_true")
     a = ap.parse_args()
@@ -338,16 +328,30 @@ def main():
     config = {"workload": f"{W['label']}, degree {deg} hexahedra, {n_per_gpu}^3 cells per GPU, {a.dtype}",
               "degree": deg, "cells_per_gpu": n_per_gpu**3, "parallelism": f"block partition x{world}",
               "l2": "working set per GPU (G + dofmap + 9 vectors, GBs) >> 126 MB L2: no flush needed"}
+    METRIC = "fused RK4 stage throughput (global dofs x stages / s)"
 
     if a.impl == "reference":
+        # the reference's CPU implementation of the path on this box's host cores: the workload's
+        # per-GPU box (the whole thing at N = 1), --steps steps after --warmup warm-ups
         if rank != 0:
             return 0
-        r = time_cpu(a.steps, a.warmup, budget_s=10.0)
-        line = {"impl": "reference", "metric": "fused RK4 stage throughput (global dofs x stages / s)",
-                "value": r["value"], "unit": "GDoF/s", "n_gpus": a.gpus, "steps": r["steps"], "warmup": max(1, a.warmup),
-                "ms_per_step": r["ms_per_step"], "steps_per_s": r["steps_per_s"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        if W["nonlinear"] or a.workload != "linear_box":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference has a CPU loop for demo_linear_box only "
+                              "(numba-cpu/demo_linear_box.py); Westervelt / piston have no CPU twin at this size"}), flush=True)
+            return 0
+        r = time_cpu(a.steps, max(1, a.warmup), n_per_gpu, deg, a.dtype, a.cpu_kind)
+        cfg = dict(config)
+        cfg["parallelism"] = f"{r['cores']} host processes, cell blocks {'x'.join(map(str, r['grid']))}, no halo exchange"
+        cfg["sample"] = r["sample"]
+        if world > 1:
+            cfg["note"] = (f"N = {world}: the CPU arm runs ONE GPU's share of the weak-scaled workload "
+                           f"({n_per_gpu}^3 cells) on this single host; GDoF/s does not depend on the box size")
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "GDoF/s", "n_gpus": a.gpus,
+                "steps": r["steps"], "warmup": r["warmup"], "ms_per_step": r["ms_per_step"],
+                "steps_per_s": r["steps_per_s"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": a.dtype, "data": "synthetic", "config": cfg,
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "impl",
+                                                   "scaling_check", "operators_sha256")},
                 "e2e": {"value": r["value"], "unit": "GDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line), flush=True)
@@ -365,6 +369,18 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (this framework has no CPU path; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+
+    if a.impl == "reference-cuda":
+        # GPU-vs-GPU anchor: the reference's Numba-CUDA kernels on this B200 beside ours
+        if rank != 0:
+            return 0
+        r = reference_cuda_arm(n_per_gpu, deg, a.dtype)
+        os.dup2(stdout_fd, 1)
+        print(json.dumps({"impl": "reference-cuda", "metric": "operator GDoF/s (stiffness, mass), reference Numba-CUDA "
+                          "kernels vs this repo on the same B200", "unit": "GDoF/s", "n_gpus": 1, "dtype": a.dtype,
+                          "data": "synthetic", **r}), flush=True)
+        return 0
+
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from fenicsx_fus_gpu_b200 import _lib
@@ -372,17 +388,6 @@ def main():
 
     dtype = np.float64 if a.dtype == "f64" else np.float32
     s = np.dtype(dtype).itemsize
-    log("building the problem")
-    solver, info = build_problem(rank, world, n_per_gpu, dtype, a.halo, a.workload, deg, a.geometry)
-    config["geometry"] = ("G streamed (reference data flow)" if a.geometry == "stream" else
-                          f"auto: {solver.nrect} rectilinear + {solver.naff - solver.nrect} affine of {solver.ncells} "
-                          "cells per GPU keep 6 geometric factors instead of 6 n^3")
-    config["parallelism"] = (f"block partition x{world}, halo: " +
-                             {"p2p": "fused put/get kernels over NVLink peer memory", "nccl": "NCCL send/recv",
-                              "none": "none (1 GPU)"}[info["halo"]])
-    solver.use_graph = not a.no_graph
-    log(f"problem built: {info['ndofs_local']} local dofs, {info['ncells_local']} cells")
-    dt = info["dt"]
     lib = _lib.lib()
 
     def barrier():
@@ -398,17 +403,59 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # ---- N > 1: is the multi-GPU path RIGHT on these GPUs?  One small global box solved on all
+    #      ranks (peer-memory halo, interior/interface overlap, graph replay) and on rank 0 alone ----
+    parity = None
+    if world > 1:
+        from fenicsx_fus_gpu_b200.selfcheck import multi_gpu_parity
+
+        log("multi-GPU parity leg")
+        pr = multi_gpu_parity(P=deg, n_per_rank=max(4, 24 // deg), dtype=dtype, nsteps=8,
+                              workload="westervelt" if W["nonlinear"] else "linear", halo_kind=a.halo,
+                              use_graph=not a.no_graph, split_cells=not a.no_split)
+        parity = {k: pr[k] for k in ("rel_l2_u", "rel_l2_v", "tol", "ok", "global_cells", "global_dofs", "steps", "halo",
+                                     "graph", "interface_cells", "shared_dofs")}
+        parity["what"] = ("one global box solved on all ranks (this run's halo, graph replay) vs the same box on "
+                          "rank 0 alone: rel-L2 of the gathered state")
+        if not pr["ok"]:
+            if rank == 0:
+                os.dup2(stdout_fd, 1)
+                print(json.dumps({"metric": METRIC, "value": None, "n_gpus": world, "multi_gpu_parity": parity,
+                                  "error": "multi-GPU parity check failed: not timing a wrong answer"}), flush=True)
+            os._exit(3)
+
+    log("building the problem")
+    solver, info = build_problem(rank, world, n_per_gpu, dtype, a.halo, a.workload, deg, a.geometry,
+                                 split_cells=not a.no_split)
+    config["geometry"] = ("G streamed (reference data flow)" if a.geometry == "stream" else
+                          f"auto: {solver.nrect} rectilinear + {solver.naff - solver.nrect} affine of {solver.ncells} "
+                          "cells per GPU keep 6 geometric factors instead of 6 n^3")
+    halo_txt = {"p2p": "fused put/get kernels over NVLink peer memory, epoch-flag signalling, exchange overlapped "
+                       "with interior-cell stiffness and the non-shared part of the close",
+                "nccl": "NCCL send/recv", "none": "none (1 GPU)"}[info["halo"]]
+    config["parallelism"] = f"block partition x{world}, halo: {halo_txt}"
+    if world > 1 and info["halo"] == "p2p":
+        config["interface_cells_per_gpu"] = int(solver.ninterface)
+        config["shared_dofs_per_gpu"] = int(solver.halo.nshared)
+    solver.use_graph = not a.no_graph
+    log(f"problem built: {info['ndofs_local']} local dofs, {info['ncells_local']} cells")
+    dt = info["dt"]
+
     # ---- device-resident timing: K graph-replayed RK4 steps ------------------
+    uuid = None
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        pass
+    cvd = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip().isdigit()]
+    clocks = Clocks(uuid or (int(cvd[local_rank]) if local_rank < len(cvd) else local_rank))
+    clocks.start()
     solver.init()
     solver.rk4(0.0, dt, warmup)  # warm-up (captures the graph)
     torch.cuda.synchronize()
     log(f"warm-up done (graph={'yes' if solver._graph is not None else 'no: ' + str(solver.graph_error)})")
     lib.fus_reset_launch_count()
     barrier()
-    cvd = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip().isdigit()]
-    clocks = Clocks(int(cvd[local_rank]) if local_rank < len(cvd) else local_rank)  # nvidia-smi index of this rank's GPU
-    clocks.start()
-    time.sleep(0.3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.time()
     barrier()
@@ -416,24 +463,51 @@ def main():
     solver.rk4(solver.t, dt, a.steps)
     e1.record()
     barrier()
-    w1 = time.time()
     elapsed = maxr(e0.elapsed_time(e1) * 1e-3)
-    clk = clocks.stop(w0, w1)
     gdofs_global = info["global_dofs"]
     value = gdofs_global * 4 * a.steps / elapsed / 1e9
+    log(f"timed region done: {elapsed * 1e3 / a.steps:.3f} ms/step")
+
+    # ---- sustained: the same steps for >= 1 s (the contract's K is short); the clocks are sampled
+    #      from the start of the timed region to the end of this one (all of it the same workload) ----
+    sustained = None
+    if a.sustain_steps > 0 and not a.no_extras:
+        ns = max(a.sustain_steps, a.steps)
+        barrier()
+        e0.record()
+        solver.rk4(solver.t, dt, ns)
+        e1.record()
+        barrier()
+        el_s = maxr(e0.elapsed_time(e1) * 1e-3)
+        sustained = {"steps": ns, "seconds": el_s, "ms_per_step": el_s / ns * 1e3,
+                     "value": gdofs_global * 4 * ns / el_s / 1e9, "unit": "GDoF/s"}
+        log(f"sustained: {sustained['ms_per_step']:.3f} ms/step over {el_s:.2f} s")
+    w1 = time.time()
+    clk = clocks.stop(w0, w1)
+    clk["window"] = "timed region + sustained run (same steps)"
+    if world > 1:  # every rank's GPU, not only rank 0's
+        allc = [None] * world
+        dist.all_gather_object(allc, clk)
+        clk = dict(clk)
+        clk["per_rank_sm_mhz"] = [c.get("sm_mhz") for c in allc]
+        clk["reasons"] = sorted({r for c in allc for r in c.get("reasons", [])})
+        clk["samples"] = int(sum(c.get("samples", 0) for c in allc))
+    if getattr(solver.halo, "p2p", False):
+        solver.halo.status()  # a timed-out wait means the numbers are meaningless: raise
+
     # kernels per step: counted once in eager mode (a graph replay bypasses the C entry points)
     lib.fus_reset_launch_count()
-    log(f"timed region done: {elapsed * 1e3 / a.steps:.3f} ms/step")
     solver.use_graph = False
     solver.rk4(solver.t, dt, 1)
     torch.cuda.synchronize()
     per_step = int(lib.fus_launch_count())
     # the dominant kernel IN SITU: the same steps launched eagerly with a CUDA-event pair around
-    # every stiffness launch (4 per step) - its duration inside the real stage sequence
+    # every stage-kernel launch (per stage: one, or interior + interface with the peer-memory halo)
     solver.probe = []
-    solver.rk4(solver.t, dt, min(a.steps, 10))
+    nprobe = min(a.steps, 10)
+    solver.rk4(solver.t, dt, nprobe)
     torch.cuda.synchronize()
-    t_in_step = float(np.mean([e_a.elapsed_time(e_b) for e_a, e_b in solver.probe])) * 1e-3
+    t_in_step = float(np.sum([e_a.elapsed_time(e_b) for e_a, e_b in solver.probe])) * 1e-3 / (4 * nprobe)
     n_probed = len(solver.probe)
     solver.probe = None
     solver.use_graph = not a.no_graph
@@ -455,7 +529,7 @@ def main():
     def e2e_step(k):
         row.copy_(tab_host[k:k + 1], non_blocking=True)  # H2D: this step's inputs
         solver.step_dev.zero_()
-        solver.replay_step(dt)
+        solver._replay_step(dt)
         check = _lib.fn("fus_pack_fwd", dtype)(solver.u.data_ptr(), sample_dev.data_ptr(), sample_idx.data_ptr(),
                                                nsample, torch.cuda.current_stream().cuda_stream)
         assert check == 0
@@ -546,8 +620,11 @@ def main():
     # back, which runs into the power cap sooner) rides along
     roofline = {"kernel": kname, "bound": "hbm", "achieved": bytes_stiff / t_in_step / 1e9, "peak": peak,
                 "unit": "GB/s", "frac": bytes_stiff / t_in_step / 1e9 / peak, "traffic": traffic,
+                "traffic_source": None if traffic is None else "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum "
+                                                               "of this kernel (profiles/stiffness_traffic.json)",
                 "peak_kind": peak_kind, "algorithmic_bytes_per_launch": bytes_stiff, "launch_ms": t_in_step * 1e3,
-                "launches_timed": n_probed, "timing": "CUDA events around every launch of the kernel inside the RK steps",
+                "launches_timed": n_probed, "timing": "CUDA events around every launch of the kernel inside the RK steps"
+                                                      + (" (interior + interface launches summed per stage)" if n_probed > 4 * nprobe else ""),
                 "standalone": {"launch_ms": t_stiff * 1e3, "launch_ms_min": t_stiff_min * 1e3, "launches_timed": reps,
                                "achieved": bytes_stiff / t_stiff / 1e9, "frac": bytes_stiff / t_stiff / 1e9 / peak,
                                "timing": "back-to-back launches between one event pair"}}
@@ -557,42 +634,45 @@ def main():
     for ea, eb in evm:
         y.zero_()
         ea.record()
-        ops.mass_operator[1, 128](x, c1, y, info["detJ"], solver.dofmap)
+        ops.mass_operator[1, 128](x, c1, y, info["detJ"], info["dofmap"])
         eb.record()
     torch.cuda.synchronize()
     t_mass = float(np.mean([ea.elapsed_time(eb) for ea, eb in evm])) * 1e-3
+    bytes_mass = nc * (nd3 * (4 + s) + s) + 2 * s * nd
     stage_bytes = solver.stage_bytes()
     stage_t = elapsed / (4 * a.steps)
 
     # ---- the operator through the C ABI with HOST buffers (fus_stiffness_host_*): x from pinned
     #      host memory, y back to pinned host memory, both copies inside the call ----
     op_host = None
-    if not W["nonlinear"] and solver.G is not None and a.geometry == "stream":
+    if not W["nonlinear"] and solver.G is not None and a.geometry == "stream" and not a.no_extras:
         xh = torch.randn(nd, dtype=solver.T).pin_memory()
         yh = torch.zeros(nd, dtype=solver.T).pin_memory()
         fh = _lib.fn("fus_stiffness_host", dtype)
         st = torch.cuda.current_stream().cuda_stream
-
-        def host_call():
-            rc = fh(xh.data_ptr(), yh.data_ptr(), nd, x.data_ptr(), y.data_ptr(), solver.cell_coeff2.data_ptr(),
-                    solver.G.data_ptr(), solver.dofmap.data_ptr(), D.data_ptr(), nc, deg, 0, st)
-            assert rc == 0
-        host_call()
-        barrier()
-        t0h = time.perf_counter()
-        nh = 5
-        for _ in range(nh):
-            host_call()  # synchronous on return
-        th = maxr((time.perf_counter() - t0h) / nh)
-        op_host = {"what": "fus_stiffness_host: y_host += K x_host (H2D x, y; kernel; D2H y) per call",
-                   "value": gdofs_global / th / 1e9, "unit": "GDoF/s", "ms_per_call": th * 1e3,
-                   "h2d_bytes_per_call": 2 * nd * s, "d2h_bytes_per_call": nd * s}
+        op_host = {}
+        for label, flags in (("accumulate", 0), ("y_zero", _lib.FUS_HOST_Y_ZERO)):
+            def host_call():
+                rc = fh(xh.data_ptr(), yh.data_ptr(), nd, x.data_ptr(), y.data_ptr(), solver.cell_coeff2.data_ptr(),
+                        solver.G.data_ptr(), solver.dofmap.data_ptr(), D.data_ptr(), nc, deg, flags, st)
+                assert rc == 0
+            host_call()
+            barrier()
+            t0h = time.perf_counter()
+            nh = 5
+            for _ in range(nh):
+                host_call()  # synchronous on return
+            th = maxr((time.perf_counter() - t0h) / nh)
+            op_host[label] = {"value": gdofs_global / th / 1e9, "unit": "GDoF/s", "ms_per_call": th * 1e3,
+                              "h2d_bytes_per_call": (2 if flags == 0 else 1) * nd * s, "d2h_bytes_per_call": nd * s}
+        op_host["what"] = ("fus_stiffness_host: y_host (+)= K x_host through the C ABI with pinned HOST buffers, copies "
+                           "inside the call; 'y_zero' = FUS_HOST_Y_ZERO (y is not uploaded, cleared on the device)")
         del xh, yh
 
     # ---- the same steps with geometry="auto" (extra, not the headline): cells with a constant
     #      Jacobian keep 6 geometric factors instead of 6 n^3 (results equal to rounding) ----
     affine = None
-    if not a.no_affine and a.geometry == "stream" and (world == 1 or info["halo"] == "nccl"):  # (the peer-memory arena holds one solver's vectors)
+    if not a.no_affine and not a.no_extras and a.geometry == "stream" and (world == 1 or info["halo"] == "nccl"):  # (the peer-memory arena holds one solver's vectors)
         del x, y
         sol2 = info["make_solver"]("auto")
         sol2.use_graph = not a.no_graph
@@ -613,7 +693,7 @@ def main():
             sol2._graph = None
 
     line = {
-        "metric": "fused RK4 stage throughput (global dofs x stages / s)", "value": value, "unit": "GDoF/s",
+        "metric": METRIC, "value": value, "unit": "GDoF/s",
         "workload": a.workload, "n_gpus": world, "steps": a.steps, "warmup": warmup, "ms_per_step": elapsed / a.steps * 1e3,
         "steps_per_s": a.steps / elapsed, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": a.dtype, "data": "synthetic", "config": {**config, "global_dofs": gdofs_global,
@@ -632,17 +712,31 @@ def main():
                                                "frac": solver.stage_bytes_survey() / stage_t / 1e9 / peak,
                                                "note": "SURVEY.md 8(d): 6s + stiffness + 8s per dof, more than "
                                                        "this implementation moves"}},
+        "sustained": sustained,
+        "multi_gpu_parity": parity,
         "e2e_operator_host_buffers": op_host,
         "affine_geometry": affine,
         "operators": {("westervelt_stage_kernel_gdofs" if W["nonlinear"] else "stiffness_gdofs"): info["ndofs_local"] / t_stiff / 1e9, "mass_gdofs": info["ndofs_local"] / t_mass / 1e9,
+                      "mass_roofline_frac": bytes_mass / t_mass / 1e9 / peak, "mass_ms": t_mass * 1e3,
                       "per_gpu_dofs": info["ndofs_local"]},
     }
     if rank == 0:
-        if world == 1 and not a.no_cpu and a.workload == "linear_box" and deg == P:
-            r = time_cpu(3, 1, budget_s=12.0)
-            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        else:
-            line["cpu_baseline"] = None
+        line["cpu_baseline"] = None
+        if world == 1 and not a.no_cpu and not a.no_extras and a.workload == "linear_box":
+            # the reference's numba-cpu path on this host's cores: the same box, 3 steps (bounded sample)
+            try:
+                r = time_cpu(3, 1, n_per_gpu, deg, a.dtype, a.cpu_kind)
+                line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "impl", "ms_per_step",
+                                                          "scaling_check", "operators_sha256")}
+                if r["impl"] == "numba":  # second, labelled figure: the reference's C++ templates in the same harness
+                    try:
+                        r2 = time_cpu(2, 1, n_per_gpu, deg, a.dtype, "cpp")
+                        if r2["impl"] == "cpp":
+                            line["cpu_baseline"]["cpp_templates"] = {k: r2[k] for k in ("value", "unit", "cores", "ms_per_step", "sample")}
+                    except Exception as e:
+                        line["cpu_baseline"]["cpp_templates"] = {"error": repr(e)[:300]}
+            except Exception as e:
+                line["cpu_baseline"] = {"error": repr(e)[:500]}
         sys.stdout.flush()
         os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)

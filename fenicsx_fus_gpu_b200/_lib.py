@@ -16,6 +16,10 @@ LIB_PATH = os.path.join(_HERE, "libfus_b200.so")
 
 _lib = None
 
+FUS_TABLES_RESIDENT = 1
+FUS_NO_ATOMICS = 2
+FUS_HOST_Y_ZERO = 4
+
 P = C.c_void_p
 I = C.c_int
 L = C.c_int64
@@ -36,7 +40,7 @@ def _sigs():
         "fus_stiffness_westervelt_rect": [P, P, P, P, P, P, P, P, P, P, P, P, L, I, I, P],
         "fus_stiffness2_affine": [P, P, P, P, P, P, P, P, P, L, I, I, P],
         "fus_stiffness2_rect": [P, P, P, P, P, P, P, P, L, I, I, P],
-        "fus_rk_close_westervelt_pw": [P, P, P, P, P, P, P, P, P, P, P, T, T, I, L, P, P],
+        "fus_rk_close_westervelt_pw": [P, P, P, P, P, P, P, P, P, P, P, T, T, I, L, P, P, P],
         "fus_compress_geometry": [P, P, P, P, P, P, L, I, T, P],
         "fus_mass": [P, P, P, P, P, L, I, P],
         "fus_axpy": [T, P, P, L, P],
@@ -50,11 +54,15 @@ def _sigs():
         "fus_unpack_rev": [P, P, P, L, P],
         "fus_pack_multi": [P, I, P, P, L, L, P],
         "fus_unpack_multi": [P, P, I, P, L, L, I, P],
-        "fus_halo_put": [P, I, P, P, P, P, L, P],
-        "fus_halo_get_add": [P, I, P, P, P, P, L, P],
+        "fus_halo_put": [P, P, I, P],
+        "fus_halo_wait_forward": [P, P, I, P],
+        "fus_halo_get_add": [P, P, I, P],
+        "fus_halo_forward": [P, P, I, P],
+        "fus_halo_reverse": [P, P, I, P],
         "fus_rk_open": [P, P, P, P, P, P, P, P, T, I, L, P],
-        "fus_rk_close": [P, P, P, P, P, P, P, P, P, T, T, I, L, P, P],
-        "fus_rk_close_westervelt": [P, P, P, P, P, P, P, P, P, P, T, T, I, L, P, P],
+        "fus_rk_close": [P, P, P, P, P, P, P, P, P, T, T, I, L, P, P, P],
+        "fus_rk_close_shared": [P, I, I, P, P, P, P, P, P, P, P, P, P, P, T, T, I, P],
+        "fus_rk_close_westervelt": [P, P, P, P, P, P, P, P, P, P, T, T, I, L, P, P, P],
         "fus_boundary_terms": [P, P, P, P, P, P, T, T, P, P, I, I, L, P],
         "fus_westervelt_mass": [P, P, P, P, P, P, P, P, L, I, P],
         "fus_geometry": [P, P, P, P, P, P, L, I, P],
@@ -66,7 +74,20 @@ def _sigs():
 
 
 #: every symbol include/fus_b200.h declares (checked by tests/test_abi.py)
-UNTYPED = ["fus_abi_version", "fus_last_error", "fus_launch_count", "fus_reset_launch_count"]
+UNTYPED = ["fus_abi_version", "fus_last_error", "fus_launch_count", "fus_reset_launch_count",
+           "fus_halo_pad_bytes", "fus_halo_create", "fus_halo_destroy", "fus_halo_num_shared",
+           "fus_halo_shared_mask", "fus_halo_status", "fus_halo_signal_reverse", "fus_halo_barrier"]
+
+
+class HaloDesc(C.Structure):
+    """``fus_halo_desc_t`` of include/fus_b200.h."""
+
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32),
+                ("n_ghost_ranks", C.c_int32), ("ghost_ranks", C.c_void_p),
+                ("n_owner_ranks", C.c_int32), ("owner_ranks", C.c_void_p),
+                ("n", C.c_int64), ("idx", C.c_void_p), ("remote_pos", C.c_void_p), ("entry_seg", C.c_void_p),
+                ("size_local", C.c_int64), ("num_ghosts", C.c_int64),
+                ("signal_pad", C.c_void_p), ("peer_pad", C.c_void_p), ("peer_delta", C.c_void_p)]
 
 
 def exported_symbols():
@@ -81,15 +102,24 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
+    from . import build as _build
 
+    if _build.needs_build():
+        # missing or older than its sources: (re)build, so a stale in-tree .so never ships
         _build.build()
     lb = C.CDLL(LIB_PATH)
     lb.fus_abi_version.restype = I
     lb.fus_last_error.restype = C.c_char_p
     lb.fus_launch_count.restype = L
     lb.fus_reset_launch_count.restype = None
+    lb.fus_halo_pad_bytes.restype, lb.fus_halo_pad_bytes.argtypes = L, [I]
+    lb.fus_halo_create.restype, lb.fus_halo_create.argtypes = I, [C.POINTER(HaloDesc), C.POINTER(C.c_void_p)]
+    lb.fus_halo_destroy.restype, lb.fus_halo_destroy.argtypes = I, [P]
+    lb.fus_halo_num_shared.restype, lb.fus_halo_num_shared.argtypes = L, [P]
+    lb.fus_halo_shared_mask.restype, lb.fus_halo_shared_mask.argtypes = P, [P]
+    lb.fus_halo_status.restype, lb.fus_halo_status.argtypes = I, [P]
+    lb.fus_halo_signal_reverse.restype, lb.fus_halo_signal_reverse.argtypes = I, [P, P]
+    lb.fus_halo_barrier.restype, lb.fus_halo_barrier.argtypes = I, [P, P]
     for base, args in _sigs().items():
         for sfx, ft in (("f64", C.c_double), ("f32", C.c_float)):
             fn = getattr(lb, f"{base}_{sfx}", None)

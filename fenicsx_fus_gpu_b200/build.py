@@ -30,6 +30,7 @@ FLAGS = [
 
 def _deps(src: str):
     d = [os.path.join(CSRC, src), os.path.join(CSRC, "fus_common.cuh"), os.path.join(CSRC, "stiffness_kernel.cuh"),
+         os.path.join(CSRC, "halo_internal.cuh"),
          os.path.join(os.path.dirname(HERE), "include", "fus_b200.h"), os.path.abspath(__file__)]
     return [p for p in d if os.path.exists(p)]
 
@@ -39,6 +40,19 @@ def _stale(target: str, deps) -> bool:
         return True
     t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
+
+
+def needs_build() -> bool:
+    """True when the library is missing, or older than any source it is built from AND a
+    compiler is at hand (a GPU box receives the prebuilt .so with fresh mtimes; without nvcc
+    the existing library is used as is)."""
+    if not os.path.exists(LIB):
+        return True
+    if not os.path.exists(NVCC):
+        return False
+    t = os.path.getmtime(LIB)
+    srcs = {p for s in SOURCES for p in _deps(s)}
+    return any(os.path.getmtime(p) > t for p in srcs)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -20,7 +20,7 @@
 
 #include <initializer_list>
 
-#include "fus_common.cuh"
+#include "halo_internal.cuh"
 
 namespace {
 
@@ -139,6 +139,9 @@ struct CloseArgs {
   int next_mode;
   long long n;
   long long* step;  // device step counter, incremented at a step boundary (may be null)
+  // multi-GPU: bit d set <=> dof d is shared with a neighbour and is closed by
+  // rk_close_shared_kernel once the reverse halo has landed (null: close everything)
+  const unsigned char* skip;
 };
 
 // WEST 0: linear (kv = b / m).  WEST 1: m += m0, kv = b / m, m = 0 (the cell-mass pair was
@@ -234,12 +237,59 @@ __global__ void __launch_bounds__(kThreads, 3) rk_close_kernel(const CloseArgs<T
   const long long stride = (long long)gridDim.x * kThreads;
   const long long i0 = (long long)blockIdx.x * kThreads + threadIdx.x;
   const long long nv = a.n / W;
-  for (long long k = i0; k < nv; k += stride) close_body<T, VEC, WEST>(a, k);
-  if constexpr (VEC) {
-    const long long k = nv * W + i0;
-    if (k < a.n) close_body<T, false, WEST>(a, k);
+  if (a.skip == nullptr) {
+    for (long long k = i0; k < nv; k += stride) close_body<T, VEC, WEST>(a, k);
+    if constexpr (VEC) {
+      const long long k = nv * W + i0;
+      if (k < a.n) close_body<T, false, WEST>(a, k);
+    }
+  } else {
+    // W divides 8: the W dofs of a pack share one mask byte
+    for (long long k = i0; k < nv; k += stride) {
+      const long long d0 = k * W;
+      const unsigned bits = ((unsigned)a.skip[d0 >> 3] >> (unsigned)(d0 & 7)) & ((1u << W) - 1u);
+      if (bits == 0u) {
+        close_body<T, VEC, WEST>(a, k);
+      } else {
+#pragma unroll
+        for (int w = 0; w < W; ++w)
+          if (!((bits >> w) & 1u)) close_body<T, false, WEST>(a, d0 + w);
+      }
+    }
+    if constexpr (VEC) {
+      const long long k = nv * W + i0;
+      if (k < a.n && !(((unsigned)a.skip[k >> 3] >> (unsigned)(k & 7)) & 1u)) close_body<T, false, WEST>(a, k);
+    }
   }
   if (a.step != nullptr && (a.next_mode == 2 || a.next_mode == 4) && i0 == 0) *a.step += 1;
+}
+
+// Multi-GPU: the stage closing on the unique owned dofs that are ghosts on a neighbour
+// (their b is complete only after the reverse halo), fused with the forward halo of the
+// NEXT stage: the fresh stage input (un, vn = ku; or the new state u, v after the last
+// stage) goes straight from registers into the neighbours' ghost slots, then the FWD epoch.
+template <typename T, int WEST>
+__global__ void __launch_bounds__(kThreads) rk_close_shared_kernel(const CloseArgs<T> a, const FusHaloDev h, int put) {
+  const long long stride = (long long)gridDim.x * kThreads;
+  T* const xa = a.next_mode == 4 ? a.u : a.un;
+  T* const xb = a.next_mode == 4 ? a.v : a.ku;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < h.nu; i += stride) {
+    const long long k = h.uniq[i];
+    close_body<T, false, WEST>(a, k);
+    if (put) {
+      const T va = xa[k], vb = xb[k];
+      for (long long j = h.uoff[i]; j < h.uoff[i + 1]; ++j) {
+        const long long dl = h.seg_delta[h.useg[j]];
+        const long long rp = h.upos[j];
+        reinterpret_cast<T*>(reinterpret_cast<char*>(xa) + dl)[rp] = va;
+        reinterpret_cast<T*>(reinterpret_cast<char*>(xb) + dl)[rp] = vb;
+      }
+    }
+  }
+  if (put) {
+    if (fus_last_block(&h.ctr[FUS_CTR_TICKET_CLOSE]))
+      fus_signal(&h.ctr[FUS_CTR_TICKET_CLOSE], &h.ctr[FUS_CTR_FWD_SENT], h.fwd_targets, h.n_ghost_ranks);
+  }
 }
 
 // b[dof[i]] += g*src[i] + dg*src2[i] + vn[dof[i]]*absb[i]; the dof list is unique
@@ -296,7 +346,7 @@ int open_entry(const T* u, const T* v, T* u0, T* v0, T* ku, const T* kv, T* un, 
 
 template <typename T, int WEST>
 int close_entry(T* u, T* v, T* u0, T* v0, T* ku, T* kv, T* un, T* b, T* m, const T* m0, T bdt,
-                T adt_next, int next_mode, int64_t n, int64_t* step, void* stream,
+                T adt_next, int next_mode, int64_t n, int64_t* step, const uint8_t* skip, void* stream,
                 const T* m2 = nullptr, const T* m5 = nullptr) {
   if (n < 0) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close: n < 0");
   if (next_mode < 0 || next_mode > 4) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close: next_mode");
@@ -306,7 +356,7 @@ int close_entry(T* u, T* v, T* u0, T* v0, T* ku, T* kv, T* un, T* b, T* m, const
   if (WEST == 2 && (m0 == nullptr || m2 == nullptr || m5 == nullptr))
     return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close_westervelt_pw: null m0 / m2 / m5");
   CloseArgs<T> a{u, v, u0, v0, ku, kv, un, b, m, m0, m2, m5, bdt, adt_next, next_mode, n,
-                 reinterpret_cast<long long*>(step)};
+                 reinterpret_cast<long long*>(step), skip};
   cudaStream_t st_ = static_cast<cudaStream_t>(stream);
   if (aligned16({u, v, u0, v0, ku, kv, un, b, m, m0, m2, m5})) {
     rk_close_kernel<T, true, WEST><<<grid_for(n / Vec<T>::W + 1), kThreads, 0, st_>>>(a);
@@ -314,6 +364,37 @@ int close_entry(T* u, T* v, T* u0, T* v0, T* ku, T* kv, T* un, T* b, T* m, const
     rk_close_kernel<T, false, WEST><<<grid_for(n), kThreads, 0, st_>>>(a);
   }
   FUS_LAUNCH_CHECK("rk_close_kernel");
+  return 0;
+}
+
+// variant 0: linear, 1: Westervelt "cells" form, 2: Westervelt pointwise form
+template <typename T>
+int close_shared_entry(fus_halo* halo, int variant, int put_next, T* u, T* v, T* u0, T* v0, T* ku, T* un, T* b,
+                       T* m, const T* m0, const T* m2, const T* m5, T bdt, T adt_next, int next_mode,
+                       void* stream) {
+  if (halo == nullptr) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close_shared: null halo handle");
+  if (variant < 0 || variant > 2) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close_shared: variant");
+  if (next_mode < 1 || next_mode > 4) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close_shared: next_mode 1..4");
+  if ((variant >= 1 && m0 == nullptr) || (variant == 2 && (m2 == nullptr || m5 == nullptr)) ||
+      (variant <= 1 && m == nullptr))
+    return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close_shared: null mass vector");
+  const FusHaloDev& h = *fus_halo_dev_of(halo);
+  if (h.nu == 0) return 0;  // nothing shared: nobody ghosts my dofs, nobody waits for my signal
+  CloseArgs<T> a{u, v, u0, v0, ku, nullptr, un, b, m, m0, m2, m5, bdt, adt_next, next_mode, h.size_local,
+                 nullptr, nullptr};
+  long long blocks = (h.nu + kThreads - 1) / kThreads;
+  const long long cap = (long long)fus_num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st_ = static_cast<cudaStream_t>(stream);
+  const int put = put_next ? 1 : 0;
+  if (variant == 0) {
+    rk_close_shared_kernel<T, 0><<<(unsigned)blocks, kThreads, 0, st_>>>(a, h, put);
+  } else if (variant == 1) {
+    rk_close_shared_kernel<T, 1><<<(unsigned)blocks, kThreads, 0, st_>>>(a, h, put);
+  } else {
+    rk_close_shared_kernel<T, 2><<<(unsigned)blocks, kThreads, 0, st_>>>(a, h, put);
+  }
+  FUS_LAUNCH_CHECK("rk_close_shared_kernel");
   return 0;
 }
 
@@ -340,21 +421,29 @@ extern "C" {
     return open_entry<T>(u, v, u0, v0, ku, kv, un, b, adt, first, n, s);                         \
   }                                                                                              \
   int fus_rk_close_##SFX(T* u, T* v, T* u0, T* v0, T* ku, T* kv, T* un, T* b, const T* m, T bdt, \
-                         T adt_next, int next_mode, int64_t n, int64_t* step_dev, void* s) {     \
+                         T adt_next, int next_mode, int64_t n, int64_t* step_dev,                \
+                         const uint8_t* skip_mask, void* s) {                                    \
     return close_entry<T, 0>(u, v, u0, v0, ku, kv, un, b, const_cast<T*>(m), nullptr, bdt,       \
-                                 adt_next, next_mode, n, step_dev, s);                           \
+                             adt_next, next_mode, n, step_dev, skip_mask, s);                    \
+  }                                                                                              \
+  int fus_rk_close_shared_##SFX(fus_halo_t* halo, int variant, int put_next, T* u, T* v, T* u0,  \
+                                T* v0, T* ku, T* un, T* b, T* m, const T* m0, const T* m2,       \
+                                const T* m5, T bdt, T adt_next, int next_mode, void* s) {        \
+    return close_shared_entry<T>(halo, variant, put_next, u, v, u0, v0, ku, un, b, m, m0, m2,    \
+                                 m5, bdt, adt_next, next_mode, s);                               \
   }                                                                                              \
   int fus_rk_close_westervelt_##SFX(T* u, T* v, T* u0, T* v0, T* ku, T* kv, T* un, T* b, T* m,   \
                                     const T* m0, T bdt, T adt_next, int next_mode, int64_t n,    \
-                                    int64_t* step_dev, void* s) {                                \
+                                    int64_t* step_dev, const uint8_t* skip_mask, void* s) {      \
     return close_entry<T, 1>(u, v, u0, v0, ku, kv, un, b, m, m0, bdt, adt_next, next_mode, n,    \
-                             step_dev, s);                                                       \
+                             step_dev, skip_mask, s);                                            \
   }                                                                                              \
   int fus_rk_close_westervelt_pw_##SFX(T* u, T* v, T* u0, T* v0, T* ku, T* kv, T* un, T* b,      \
                                        const T* m0, const T* m2, const T* m5, T bdt, T adt_next, \
-                                       int next_mode, int64_t n, int64_t* step_dev, void* s) {   \
+                                       int next_mode, int64_t n, int64_t* step_dev,              \
+                                       const uint8_t* skip_mask, void* s) {                      \
     return close_entry<T, 2>(u, v, u0, v0, ku, kv, un, b, nullptr, m0, bdt, adt_next, next_mode, \
-                             n, step_dev, s, m2, m5);                                            \
+                             n, step_dev, skip_mask, s, m2, m5);                                 \
   }                                                                                              \
   int fus_boundary_terms_##SFX(T* b, const T* vn, const int32_t* dof, const T* src,              \
                                const T* src2, const T* absb, T g, T dg, const T* gtab,           \

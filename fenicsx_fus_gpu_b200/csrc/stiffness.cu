@@ -80,6 +80,164 @@ int stiffness_entry(const T* xa, const T* ca, const T* xb, const T* cb, T* y, co
   return mode == 1 ? launch<T, 1, 0>(a, P, flags, st) : launch<T, 0, 0>(a, P, flags, st);
 }
 
+// ---- host-buffer entry point: H2D of x (and y), the action, D2H of y, pipelined -------------
+//
+// The cells are cut into kHostChunks ranges.  A reduction over the dofmap gives the dof interval
+// [lo_c, hi_c] every range touches; with H_c = max_{c' <= c} hi_c' and L_c = min_{c' >= c} lo_c',
+// range c may run as soon as x[0, H_c] has arrived, and y[0, L_{c+1}) is final as soon as range c
+// has run.  So the upload of piece c+1, the kernel of range c and the download of what range c-1
+// finished proceed concurrently on three streams (PCIe is full duplex).  On a mesh whose cell
+// order follows its dof order (every box mesh here, any mesh after a bandwidth-reducing
+// renumbering) the pieces are ~1/kHostChunks of the vectors; on an unordered mesh H_0 ~ nd and
+// the pipeline degenerates, correctly, into upload -> action -> download.
+constexpr int kHostChunks = 8;
+
+__global__ void __launch_bounds__(256) dof_range_kernel(const int32_t* __restrict__ dofmap, long long ncells,
+                                                        int Nd, long long cells_per_chunk, int* lo, int* hi) {
+  const int c = blockIdx.y;
+  const long long c0 = c * cells_per_chunk;
+  long long c1 = c0 + cells_per_chunk;
+  if (c1 > ncells) c1 = ncells;
+  const long long e0 = c0 * Nd, e1 = c1 * Nd;
+  int mn = 0x7fffffff, mx = -1;
+  for (long long e = e0 + (long long)blockIdx.x * 256 + threadIdx.x; e < e1; e += (long long)gridDim.x * 256) {
+    const int d = dofmap[e];
+    mn = d < mn ? d : mn;
+    mx = d > mx ? d : mx;
+  }
+  mn = __reduce_min_sync(0xffffffffu, mn);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(lo + c, mn);
+    atomicMax(hi + c, mx);
+  }
+}
+
+struct HostPipe {
+  cudaStream_t in = nullptr, out = nullptr;
+  cudaEvent_t start = nullptr, up[kHostChunks] = {}, done[kHostChunks] = {}, fin = nullptr;
+  int* ranges_dev = nullptr;   // lo[kHostChunks], hi[kHostChunks]
+  int* ranges_host = nullptr;  // pinned
+  bool ok = false;
+};
+
+HostPipe* host_pipe() {
+  static HostPipe pipes[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  HostPipe& p = pipes[dev];
+  if (!p.ok) {
+    bool good = cudaStreamCreateWithFlags(&p.in, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&p.out, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaEventCreateWithFlags(&p.start, cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&p.fin, cudaEventDisableTiming) == cudaSuccess &&
+                cudaMalloc(&p.ranges_dev, 2 * kHostChunks * sizeof(int)) == cudaSuccess &&
+                cudaMallocHost(&p.ranges_host, 2 * kHostChunks * sizeof(int)) == cudaSuccess;
+    for (int c = 0; c < kHostChunks && good; ++c)
+      good = cudaEventCreateWithFlags(&p.up[c], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&p.done[c], cudaEventDisableTiming) == cudaSuccess;
+    if (!good) return nullptr;
+    p.ok = true;
+  }
+  return &p;
+}
+
+template <typename T>
+int stiffness_host(const T* x_host, T* y_host, int64_t nd, T* x_dev, T* y_dev, const T* coeff, const T* G,
+                   const int32_t* dofmap, const T* dphi, int64_t ncells, int P, int flags, void* stream) {
+  if (ncells < 0 || nd < 0) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "stiffness_host: negative size");
+  if (P < 2 || P > 7) return fus_set_error(FUS_ERR_BAD_DEGREE, "stiffness_host: degree must be 2..7");
+  if (nd == 0) return 0;
+  if (x_host == nullptr || y_host == nullptr || x_dev == nullptr || y_dev == nullptr)
+    return fus_set_error(FUS_ERR_BAD_ARGUMENT, "stiffness_host: null buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool yzero = (flags & FUS_HOST_Y_ZERO) != 0;
+  const int kflags = flags & ~FUS_HOST_Y_ZERO;
+  const int Nd = (P + 1) * (P + 1) * (P + 1);
+  HostPipe* hp = host_pipe();
+  // cells per range: even, so that every range's G slice keeps the 16-byte alignment of the base
+  long long cpc = ((ncells + kHostChunks - 1) / kHostChunks + 1) / 2 * 2;
+  if (hp == nullptr || ncells < 64 * kHostChunks) {
+    // tiny problems (or no side streams): upload, action, download on the caller's stream
+    FUS_CUDA(cudaMemcpyAsync(x_dev, x_host, sizeof(T) * nd, cudaMemcpyHostToDevice, st));
+    if (yzero) {
+      FUS_CUDA(cudaMemsetAsync(y_dev, 0, sizeof(T) * nd, st));
+    } else {
+      FUS_CUDA(cudaMemcpyAsync(y_dev, y_host, sizeof(T) * nd, cudaMemcpyHostToDevice, st));
+    }
+    if (int rc = stiffness_entry<T>(x_dev, coeff, nullptr, nullptr, y_dev, G, dofmap, dphi, ncells, P, kflags, stream, 0))
+      return rc;
+    FUS_CUDA(cudaMemcpyAsync(y_host, y_dev, sizeof(T) * nd, cudaMemcpyDeviceToHost, st));
+    FUS_CUDA(cudaStreamSynchronize(st));
+    return 0;
+  }
+  // 1. dof interval of every cell range (one pass over the dofmap on the device)
+  int init[2 * kHostChunks];
+  for (int c = 0; c < kHostChunks; ++c) {
+    init[c] = 0x7fffffff;
+    init[kHostChunks + c] = -1;
+  }
+  FUS_CUDA(cudaMemcpyAsync(hp->ranges_dev, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  dof_range_kernel<<<dim3(64, kHostChunks), 256, 0, st>>>(dofmap, ncells, Nd, cpc, hp->ranges_dev,
+                                                         hp->ranges_dev + kHostChunks);
+  FUS_LAUNCH_CHECK("dof_range_kernel");
+  FUS_CUDA(cudaMemcpyAsync(hp->ranges_host, hp->ranges_dev, sizeof(init), cudaMemcpyDeviceToHost, st));
+  if (yzero) FUS_CUDA(cudaMemsetAsync(y_dev, 0, sizeof(T) * nd, st));
+  if (!(kflags & FUS_TABLES_RESIDENT)) {
+    if (int rc = set_dphi<T>(P, dphi, st)) return rc;
+  }
+  FUS_CUDA(cudaEventRecord(hp->start, st));
+  FUS_CUDA(cudaStreamSynchronize(st));
+  long long H[kHostChunks], L[kHostChunks + 1];
+  long long run = -1;
+  for (int c = 0; c < kHostChunks; ++c) {
+    const long long hi = hp->ranges_host[kHostChunks + c];
+    if (hi >= nd) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "stiffness_host: dofmap entry >= nd");
+    run = hi > run ? hi : run;
+    H[c] = run + 1;  // x[0, H_c) must be resident before range c
+  }
+  H[kHostChunks - 1] = nd;
+  L[kHostChunks] = nd;
+  for (int c = kHostChunks - 1; c >= 0; --c) {
+    long long lo = hp->ranges_host[c];
+    if (lo == 0x7fffffff) lo = nd;  // empty range
+    L[c] = lo < L[c + 1] ? lo : L[c + 1];
+  }
+  // 2. three-stream pipeline
+  FUS_CUDA(cudaStreamWaitEvent(hp->in, hp->start, 0));
+  FUS_CUDA(cudaStreamWaitEvent(hp->out, hp->start, 0));
+  long long up0 = 0, down0 = 0;
+  for (int c = 0; c < kHostChunks; ++c) {
+    const long long c0 = c * cpc;
+    long long nc = ncells - c0;
+    if (nc > cpc) nc = cpc;
+    if (H[c] > up0) {
+      FUS_CUDA(cudaMemcpyAsync(x_dev + up0, x_host + up0, sizeof(T) * (H[c] - up0), cudaMemcpyHostToDevice, hp->in));
+      if (!yzero)
+        FUS_CUDA(cudaMemcpyAsync(y_dev + up0, y_host + up0, sizeof(T) * (H[c] - up0), cudaMemcpyHostToDevice, hp->in));
+      up0 = H[c];
+    }
+    FUS_CUDA(cudaEventRecord(hp->up[c], hp->in));
+    FUS_CUDA(cudaStreamWaitEvent(st, hp->up[c], 0));
+    if (nc > 0) {
+      if (int rc = stiffness_entry<T>(x_dev, coeff + c0, nullptr, nullptr, y_dev, G + c0 * (long long)Nd * 6,
+                                      dofmap + c0 * (long long)Nd, dphi, nc, P, kflags | FUS_TABLES_RESIDENT, stream, 0))
+        return rc;
+    }
+    FUS_CUDA(cudaEventRecord(hp->done[c], st));
+    const long long fin = L[c + 1];  // y[0, fin) is final now
+    if (fin > down0) {
+      FUS_CUDA(cudaStreamWaitEvent(hp->out, hp->done[c], 0));
+      FUS_CUDA(cudaMemcpyAsync(y_host + down0, y_dev + down0, sizeof(T) * (fin - down0), cudaMemcpyDeviceToHost, hp->out));
+      down0 = fin;
+    }
+  }
+  FUS_CUDA(cudaEventRecord(hp->fin, hp->out));
+  FUS_CUDA(cudaStreamWaitEvent(st, hp->fin, 0));
+  FUS_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -136,26 +294,12 @@ int fus_stiffness_host_f64(const double* x_host, double* y_host, int64_t nd, dou
                            double* y_dev, const double* coeff, const double* G,
                            const int32_t* dofmap, const double* dphi, int64_t ncells, int P,
                            int flags, void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  FUS_CUDA(cudaMemcpyAsync(x_dev, x_host, sizeof(double) * nd, cudaMemcpyHostToDevice, st));
-  FUS_CUDA(cudaMemcpyAsync(y_dev, y_host, sizeof(double) * nd, cudaMemcpyHostToDevice, st));
-  int rc = fus_stiffness_f64(x_dev, coeff, y_dev, G, dofmap, dphi, ncells, P, flags, stream);
-  if (rc) return rc;
-  FUS_CUDA(cudaMemcpyAsync(y_host, y_dev, sizeof(double) * nd, cudaMemcpyDeviceToHost, st));
-  FUS_CUDA(cudaStreamSynchronize(st));
-  return 0;
+  return stiffness_host<double>(x_host, y_host, nd, x_dev, y_dev, coeff, G, dofmap, dphi, ncells, P, flags, stream);
 }
 int fus_stiffness_host_f32(const float* x_host, float* y_host, int64_t nd, float* x_dev,
                            float* y_dev, const float* coeff, const float* G, const int32_t* dofmap,
                            const float* dphi, int64_t ncells, int P, int flags, void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  FUS_CUDA(cudaMemcpyAsync(x_dev, x_host, sizeof(float) * nd, cudaMemcpyHostToDevice, st));
-  FUS_CUDA(cudaMemcpyAsync(y_dev, y_host, sizeof(float) * nd, cudaMemcpyHostToDevice, st));
-  int rc = fus_stiffness_f32(x_dev, coeff, y_dev, G, dofmap, dphi, ncells, P, flags, stream);
-  if (rc) return rc;
-  FUS_CUDA(cudaMemcpyAsync(y_host, y_dev, sizeof(float) * nd, cudaMemcpyDeviceToHost, st));
-  FUS_CUDA(cudaStreamSynchronize(st));
-  return 0;
+  return stiffness_host<float>(x_host, y_host, nd, x_dev, y_dev, coeff, G, dofmap, dphi, ncells, P, flags, stream);
 }
 
 }  // extern "C"

@@ -29,6 +29,7 @@ def _to_dev(a, dtype):
     if isinstance(a, np.ndarray):
         return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).cuda(), True
     if isinstance(a, torch.Tensor):
+        _lib.dev(a, dtype)  # CUDA, contiguous, and of the expected dtype: never reinterpret silently
         return a, False
     d = _lib.dev(a)  # __cuda_array_interface__ object
     if d.dtype != np.dtype(dtype):

@@ -47,6 +47,7 @@ class Setup:
     halo: object | None
     dev: dict = field(default_factory=dict)  # device tensors: dofmap, G, detJ, x_dofs, x_g, tables
     h: float = 0.0
+    local_to_serial: np.ndarray | None = None  # (ndofs,) index of every local dof in the unpartitioned box
 
 
 def _d(a):
@@ -72,6 +73,7 @@ def box_setup(P, ncells, lengths, dtype=np.float64, rank=0, world=1, comm=None, 
         lengths = (float(lengths),) * 3
     tb = S.element_tables(P, order, dtype)
     halo = None
+    l2s = None
     if world == 1:
         mesh = S.create_box(ncells, lengths, dtype=dtype, perturb=perturb, seed=seed)
         dofmap = S.tensor_dofmap(mesh, P, order)
@@ -80,6 +82,7 @@ def box_setup(P, ncells, lengths, dtype=np.float64, rank=0, world=1, comm=None, 
         part = S.partition_box(ncells, P, world, lengths=lengths, order=order, dtype=dtype,
                                perturb=perturb, seed=seed, ranks=[rank], grid=grid)[0]
         mesh, dofmap = part.mesh, part.dofmap
+        l2s = part.local_to_serial
         nlocal = part.index_map.size_local
         ndofs = nlocal + part.index_map.num_ghosts
         if scatter_data is not None:  # ranks emulated in one process: lists computed for all ranks at once
@@ -103,7 +106,7 @@ def box_setup(P, ncells, lengths, dtype=np.float64, rank=0, world=1, comm=None, 
     pre.compute_geometry(dev["G"], dev["detJ"], (dev["x_dofs"], dev["x_g"]), nc, dev["dphi"], dev["wts"])
     h = min(lengths[i] / ncells[i] for i in range(3))
     return Setup(P, dtype, rank, world, mesh, tb, dofmap, ndofs, nlocal, S.num_dofs(ncells, P),
-                 tuple(ncells), halo, dev, h)
+                 tuple(ncells), halo, dev, h, l2s)
 
 
 def facet_group(su: Setup, local_facets, predicate=None):

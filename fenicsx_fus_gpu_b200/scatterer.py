@@ -376,7 +376,11 @@ def scatter_reverse(comm, owners_data, ghosts_data, N, float_type):
 class SymmFabric:
     """Peer-addressable device memory for one process per GPU: a symmetric
     arena (``torch.distributed._symmetric_memory``: CUDA VMM allocations mapped
-    into every peer over NVLink/NVSwitch) plus its signal-pad barrier."""
+    into every peer over NVLink/NVSwitch).  torch provides the allocation and
+    the rendezvous only; signalling and data movement are this library's own
+    kernels (csrc/halo.cu)."""
+
+    emulated = False
 
     def __init__(self, arena_bytes: int, group=None):
         import torch
@@ -390,10 +394,12 @@ class SymmFabric:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)  # same size everywhere
         self.arena_bytes = (int(t.item()) + 255) // 256 * 256
         self.arena = symm.empty(self.arena_bytes, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+        self.arena.zero_()
         self.hdl = symm.rendezvous(self.arena, self.group)
         self.base = [int(p) for p in self.hdl.buffer_ptrs]
         self._used = 0
-        self._channel = 0
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)  # every arena is zeroed before anybody stores into it
 
     def alloc(self, numel: int, tdtype, slot_numel: int | None = None):
         """Carve a tensor out of the arena.  Every rank must make the same
@@ -413,8 +419,15 @@ class SymmFabric:
     def peer_ptr(self, rank: int, t):
         return self.base[rank] + (t.data_ptr() - self.base[self.rank])
 
-    def barrier(self):
-        self.hdl.barrier(channel=0)
+    def host_sync(self):
+        """Real GPUs run concurrently: nothing to do (see ``_LocalFabric.host_sync``)."""
+
+    def host_barrier(self):
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
 
     def max_over_ranks(self, v: int) -> int:
         import torch
@@ -432,7 +445,12 @@ class SymmFabric:
 
 class _LocalFabric:
     """The same interface with the ranks emulated by threads of one process on
-    one GPU: a peer's memory is just another local buffer."""
+    one GPU: a peer's memory is just another local buffer.  All ranks enqueue
+    on ONE stream, so a kernel that waits for a flag must be enqueued after the
+    kernel that raises it: ``host_sync`` (a thread barrier) is called by the
+    exchange before it enqueues a wait."""
+
+    emulated = True
 
     def __init__(self, cluster: LocalCluster, rank: int, arena_bytes: int):
         import torch
@@ -450,9 +468,11 @@ class _LocalFabric:
     alloc = SymmFabric.alloc
     peer_ptr = SymmFabric.peer_ptr
 
-    def barrier(self):
+    def host_sync(self):
         # every rank has ENQUEUED its work on the shared stream: stream order does the rest
         self.cluster._barrier.wait()
+
+    host_barrier = host_sync
 
     def max_over_ranks(self, v: int) -> int:
         cl = self.cluster
@@ -478,20 +498,36 @@ def local_fabric(cluster: LocalCluster, rank: int, arena_bytes: int):
     return _LocalFabric(cluster, rank, arena_bytes)
 
 
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 class P2PHaloExchange:
-    """Halo exchange fused into two kernels over NVLink peer memory.
+    """Halo exchange fused into kernels over NVLink peer memory, behind the
+    C-ABI handle ``fus_halo_t`` (include/fus_b200.h, csrc/halo.cu).
 
-    forward  = ``fus_halo_put`` (owned values stored straight into the peers'
-    ghost slots) + one barrier; reverse = barrier + ``fus_halo_get_add`` (ghost
-    partial sums loaded straight from the peers and added) + barrier.  No
-    staging buffers, no NCCL, no pack/unpack launches: 2 + 3 small launches per
-    RK stage instead of 2 x (pack + grouped send/recv + unpack).
+    Data: ``put`` stores owned values straight into the neighbours' ghost
+    slots; ``get_add`` loads the neighbours' ghost partial sums straight from
+    their vectors and adds them.  Ordering: per-neighbour epoch flags raised
+    and awaited by the kernels themselves (``st.release.sys`` /
+    ``ld.acquire.sys``) - no global barrier, no NCCL, no host synchronisation,
+    capturable in a CUDA graph.
 
-    Vectors that take part (``un``, ``vn``, ``b``, ``m``) must be allocated
-    with ``alloc`` so that every peer can address them.  Because peers write
-    into the ghost slots directly, the owner of a vector must not write its own
-    ghost region between exchanges (the fused solvers update owned entries only
-    when this exchange is used).
+    * ``forward(*vecs)`` / ``reverse(*vecs)`` are the reference's
+      ``scatter_forward`` / ``scatter_reverse`` (cuda/scatterer.py:104-277),
+      safe in any call sequence that all ranks make identically.
+    * ``put / wait_forward / signal_reverse / get_add`` are the split-phase
+      pieces the fused solvers interleave with interior-cell work; ``fork`` /
+      ``join`` / ``side`` put the exchange on a second stream.
+
+    Vectors that take part must be allocated with ``alloc`` (same offset of a
+    symmetric arena on every rank).  Peers write the ghost slots directly, so
+    the owner of a vector must not write its own ghost region between
+    exchanges (the fused solvers update owned entries only).
     """
 
     p2p = True
@@ -499,73 +535,160 @@ class P2PHaloExchange:
     def __init__(self, fabric, owners_data, ghosts_data, N, nghost, float_type):
         import torch
 
+        lib = _lib.lib()
         self.fabric = fabric
         self.N, self.nghost = int(N), int(nghost)
         self.dtype = np.dtype(float_type)
         self.tdtype = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32}[self.dtype]
         o_idx, o_size, o_ranks = owners_data
         g_idx, g_size, g_ranks = ghosts_data
-        self.ghost_ranks = [int(r) for r in np.asarray(g_ranks).ravel()]
+        self.ghost_ranks = np.ascontiguousarray(np.asarray(g_ranks).ravel(), dtype=np.int32)
+        self.owner_ranks = np.ascontiguousarray(np.asarray(o_ranks).ravel(), dtype=np.int32)
         ghost_sizes = [int(s) for s in np.asarray(g_size).ravel()]
-        dev = torch.device("cuda", torch.cuda.current_device())
-        self.idx = _cat_index(g_idx).to(dev)
-        self.n = int(self.idx.numel())
+        idx = _cat_index(g_idx).numpy()
+        self.n = int(idx.size)
         # where each of my shared dofs sits in the neighbour's vector: the neighbour's
         # owners_idx list for me (same order as my ghosts_idx, cuda/utils.py:57-73) + its N
         send = [np.ascontiguousarray(np.asarray(ix, dtype=np.int64) + self.N) for ix in o_idx]
-        recv = fabric.exchange_index_lists(send, [int(r) for r in np.asarray(o_ranks).ravel()],
-                                           ghost_sizes, self.ghost_ranks)
-        self.remote_pos = _cat_index([np.asarray(r, dtype=np.int64) for r in recv]).to(dev)
+        recv = fabric.exchange_index_lists(send, [int(r) for r in self.owner_ranks], ghost_sizes,
+                                           [int(r) for r in self.ghost_ranks])
+        remote_pos = _cat_index([np.asarray(r, dtype=np.int64) for r in recv]).numpy()
         seg = np.repeat(np.arange(len(ghost_sizes), dtype=np.int32), ghost_sizes)
-        self.entry_seg = torch.from_numpy(seg).to(dev)
         self.slot = fabric.max_over_ranks(self.N + self.nghost)
-        self._tables = {}
-        self._ptrs = (C.c_void_p * 4)()
+        world = fabric.size
+        self.pad = fabric.alloc(int(lib.fus_halo_pad_bytes(world)), torch.uint8)
+        peer_pad = np.array([fabric.peer_ptr(q, self.pad) for q in range(world)], dtype=np.uint64)
+        peer_delta = np.array([fabric.base[q] - fabric.base[fabric.rank] for q in range(world)], dtype=np.int64)
+        keep = [np.ascontiguousarray(a) for a in (idx.astype(np.int64), remote_pos.astype(np.int64), seg)]
+        d = _lib.HaloDesc()
+        d.rank, d.world = fabric.rank, world
+        d.n_ghost_ranks, d.ghost_ranks = int(self.ghost_ranks.size), self.ghost_ranks.ctypes.data
+        d.n_owner_ranks, d.owner_ranks = int(self.owner_ranks.size), self.owner_ranks.ctypes.data
+        d.n, d.idx, d.remote_pos, d.entry_seg = self.n, keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data
+        d.size_local, d.num_ghosts = self.N, self.nghost
+        d.signal_pad = self.pad.data_ptr()
+        d.peer_pad, d.peer_delta = peer_pad.ctypes.data, peer_delta.ctypes.data
+        torch.cuda.synchronize()  # the pad is zeroed before the handle (and any neighbour) can use it
+        h = C.c_void_p()
+        check(lib.fus_halo_create(C.byref(d), C.byref(h)), "fus_halo_create")
+        self._h = h
+        self._lib = lib
+        self.nshared = int(lib.fus_halo_num_shared(h))
+        self.shared_mask = lib.fus_halo_shared_mask(h)  # device address of the bitmask
+        self._side = None
+        fabric.host_barrier()  # every rank's pad and handle exist before the first signal
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._lib.fus_halo_destroy(h)
+            except Exception:  # interpreter shutdown
+                pass
 
     @staticmethod
     def arena_bytes(ndofs_local: int, float_type, nvec: int = 12) -> int:
-        """Arena size for ``nvec`` exchanged vectors of ``ndofs_local`` entries."""
-        return nvec * ((int(ndofs_local) * np.dtype(float_type).itemsize + 255) // 256 * 256 + 256)
+        """Arena size for ``nvec`` exchanged vectors of ``ndofs_local`` entries (+ the signal pad)."""
+        return nvec * ((int(ndofs_local) * np.dtype(float_type).itemsize + 255) // 256 * 256 + 256) + 4096
 
     def alloc(self):
         """A zeroed ``(N + nghost,)`` vector in peer-addressable memory."""
         return self.fabric.alloc(self.N + self.nghost, self.tdtype, self.slot)
 
-    def _peer_table(self, vecs):
-        import torch
+    @property
+    def handle(self):
+        return self._h
 
-        key = tuple(v.data_ptr() for v in vecs)
-        tab = self._tables.get(key)
-        if tab is None:
-            rows = [[self.fabric.peer_ptr(q, v) for v in vecs] for q in self.ghost_ranks]
-            # int64 view of the (unsigned) device addresses
-            tab = torch.tensor(np.array(rows, dtype=np.uint64).astype(np.int64).reshape(-1)
-                               if rows else np.zeros(0, np.int64), device=self.idx.device)
-            self._tables[key] = tab
-        return tab
+    def _vecs(self, vecs, lo=1):
+        if not lo <= len(vecs) <= 4:
+            raise ValueError(f"P2PHaloExchange: {lo}..4 vectors per round")
+        arr = (C.c_void_p * 4)()
+        for i, v in enumerate(vecs):
+            arr[i] = dev(v, self.dtype).ptr
+        return arr
 
-    def _launch(self, name, vecs):
-        if not 1 <= len(vecs) <= 4:
-            raise ValueError("P2PHaloExchange: 1..4 vectors per round")
-        if self.n:
-            tab = self._peer_table(vecs)
-            for i, v in enumerate(vecs):
-                self._ptrs[i] = dev(v, self.dtype).ptr
-            check(fn(name, self.dtype)(self._ptrs, len(vecs), tab.data_ptr(), self.idx.data_ptr(),
-                                       self.remote_pos.data_ptr(), self.entry_seg.data_ptr(), self.n,
-                                       current_stream()), name)
+    # -- split-phase pieces ------------------------------------------------------
+    def put(self, *vecs):
+        """Owner values -> the neighbours' ghost slots, then the FWD epoch."""
+        check(fn("fus_halo_put", self.dtype)(self._h, self._vecs(vecs), len(vecs), current_stream()), "fus_halo_put")
+
+    def wait_forward(self, *zero_vecs):
+        """Wait for the puts of every owner of my ghosts; then clear the ghost part of ``zero_vecs``."""
+        self.fabric.host_sync()
+        check(fn("fus_halo_wait_forward", self.dtype)(self._h, self._vecs(zero_vecs, 0), len(zero_vecs),
+                                                      current_stream()), "fus_halo_wait_forward")
+
+    def signal_reverse(self):
+        """REV epoch -> the owners of my ghosts: my ghost partial sums are complete."""
+        check(self._lib.fus_halo_signal_reverse(self._h, current_stream()), "fus_halo_signal_reverse")
+
+    def get_add(self, *vecs):
+        """Wait for every ghosting neighbour's REV epoch, then add their partial sums."""
+        self.fabric.host_sync()
+        check(fn("fus_halo_get_add", self.dtype)(self._h, self._vecs(vecs), len(vecs), current_stream()),
+              "fus_halo_get_add")
 
     def barrier(self):
-        self.fabric.barrier()
+        """Neighbour barrier on the current stream (a host barrier when the ranks are emulated
+        on one stream, where a waiting kernel would block the kernel it waits for)."""
+        if self.fabric.emulated:
+            self.fabric.host_sync()
+        else:
+            check(self._lib.fus_halo_barrier(self._h, current_stream()), "fus_halo_barrier")
 
+    def status(self):
+        """Raises if a wait ran into the time-out (a neighbour died).  Synchronises."""
+        check(self._lib.fus_halo_status(self._h), "fus_halo_status")
+
+    # -- the reference's two exchanges -----------------------------------------------
     def forward(self, *vecs):
         """Owner values -> every ghost copy (cuda/scatterer.py:191-277)."""
-        self._launch("fus_halo_put", vecs)
-        self.fabric.barrier()
+        if self.fabric.emulated:
+            self.barrier()
+            self.put(*vecs)
+            self.wait_forward()
+        else:
+            check(fn("fus_halo_forward", self.dtype)(self._h, self._vecs(vecs), len(vecs), current_stream()),
+                  "fus_halo_forward")
 
     def reverse(self, *vecs):
         """Ghost partial sums added into the owners (cuda/scatterer.py:104-188).
         The ghost region keeps its values, as in the reference."""
-        self.fabric.barrier()  # every rank's ghost sums are complete
-        self._launch("fus_halo_get_add", vecs)
-        self.fabric.barrier()  # every rank has read them: they may be overwritten now
+        if self.fabric.emulated:
+            self.signal_reverse()
+            self.get_add(*vecs)
+            self.barrier()
+        else:
+            check(fn("fus_halo_reverse", self.dtype)(self._h, self._vecs(vecs), len(vecs), current_stream()),
+                  "fus_halo_reverse")
+
+    # -- second stream for the exchange (real GPUs only) -----------------------------
+    @property
+    def concurrent(self):
+        return not self.fabric.emulated
+
+    def _side_stream(self):
+        import torch
+
+        if self._side is None:
+            self._side = torch.cuda.Stream(priority=-1)
+        return self._side
+
+    def fork(self):
+        """Later work under ``side()`` is ordered after everything enqueued so far."""
+        import torch
+
+        if self.concurrent:
+            self._side_stream().wait_stream(torch.cuda.current_stream())
+
+    def side(self):
+        import torch
+
+        return torch.cuda.stream(self._side_stream()) if self.concurrent else _NullCtx()
+
+    def join(self):
+        """Later work on the current stream is ordered after the work under ``side()``."""
+        import torch
+
+        if self.concurrent:
+            torch.cuda.current_stream().wait_stream(self._side_stream())

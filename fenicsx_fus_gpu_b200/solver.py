@@ -26,6 +26,19 @@ per step instead of 48, same arithmetic bit for bit.  Source
 amplitudes come from a device table indexed by a device step counter, so a
 replay needs no host work at all.
 
+Multi-GPU (peer-memory halo, ``scatterer.P2PHaloExchange``): the cells are split at set-up
+into *interior* ones and *interface* ones (those touching a ghost dof), and a stage becomes
+
+    main stream                                   exchange stream
+    interior cells                          ||    wait for the neighbours' puts; clear ghost b
+    interface cells, boundary terms, "my ghost sums are ready" signal
+    close on the dofs nobody shares         ||    get_add (ghost sums -> owners), close on the
+                                                  shared dofs + put of the next stage input
+
+so neither the forward nor the reverse exchange of cuda/demo_linear_box.py:536-553 is ever
+waited for on the critical path, and there is no barrier: the ordering is per-neighbour
+epoch flags raised by the kernels themselves (csrc/halo.cu).
+
 Reference quirks: the source is evaluated at the stage
 time ``tn`` as the numba-cpu / C++ paths do (Q1; ``source_at_stage_time=False``
 gives the CUDA demos' behaviour); the solution is ``u`` (Q2); vector kernels
@@ -34,10 +47,16 @@ run over owned + ghost entries and ghost ``m`` keeps its partial sums (Q3).
 
 from __future__ import annotations
 
+from collections import namedtuple
+
 import numpy as np
 
 from . import _lib
 from ._lib import check, current_stream, fn
+
+# a contiguous range of (permuted) cells that one kernel launch covers:
+# kind 0 rectilinear, 1 affine, 2 streamed G; c0/n cell range; g0 first row of the streamed G / detJ arrays
+Seg = namedtuple("Seg", "kind c0 n g0")
 
 A_RUNGE = (0.0, 0.5, 0.5, 1.0)
 B_RUNGE = (1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0)
@@ -99,7 +118,8 @@ class _RK4:
     westervelt = False
 
     def __init__(self, P, float_type, ndofs, dofmap, G, dphi_1D, halo=None, source=None,
-                 source_at_stage_time=True, use_graph=True, geometry="stream", weights=None):
+                 source_at_stage_time=True, use_graph=True, geometry="stream", weights=None,
+                 split_cells=True):
         torch = _torch()
         if not torch.cuda.is_available():
             raise _lib.FusError("no CUDA device: this package has no CPU path")
@@ -123,6 +143,9 @@ class _RK4:
         # slots are written by the neighbours.
         self._m_accum = False  # Westervelt "cells" form: m is accumulated per stage (and reverse-exchanged)
         self.p2p = bool(getattr(halo, "p2p", False))
+        # peer-memory halo: launch interior cells (no ghost dof) while the forward exchange is in
+        # flight and interface cells after it (False: one launch after the exchange, for A/B runs)
+        self.split_cells = bool(split_cells)
         self.nupd = int(halo.N) if self.p2p else self.ndofs  # entries the vector kernels update
         zx = halo.alloc if self.p2p else z
         # the reference's 14 vectors (cuda/demo_linear_box.py:380-385, 464-471)
@@ -155,10 +178,15 @@ class _RK4:
             raise ValueError("geometry='auto' needs the quadrature weights (n^3,)")
         self.geometry = geometry
         self._weights = None if weights is None else _dev(weights, self.T)
-        self.nrect = 0  # cells [0, nrect) are rectilinear (affine, diagonal Gc), after the set-up permutation
-        self.naff = 0  # cells [0, naff) are affine: [nrect, naff) go through the general affine kernel
+        self.nrect = 0  # number of rectilinear cells (affine, diagonal Gc)
+        self.naff = 0  # number of affine cells (rectilinear ones included)
         self.Gc = self.detJc = None
         self._rect_tables = None
+        self.cell_perm = None
+        # cell ranges per launch phase: "all" on one GPU / with the NCCL halo; "interior" (no ghost
+        # dof) and "interface" with the peer-memory halo, whose exchange overlaps the interior cells
+        self._phases = {"all": [Seg(2, 0, self.ncells, 0)]}
+        self.ninterface = 0
 
     # the solution between steps (device tensors; write initial data into them before rk4)
     @property
@@ -218,51 +246,78 @@ class _RK4:
             setattr(self, "_" + slot, tmp[idx].contiguous())
 
     def _setup_geometry(self, detJ, cell_arrays):
-        """geometry='auto': classify the cells, move the affine ones to the front of every
-        per-cell array (``cell_arrays``: attribute names of (Nc,) / (Nc, n^3) tensors; the dofmap
-        and G are handled here), keep G / detJ for the remaining cells only.  Summation order
-        inside the atomics aside, a cell permutation does not change the result."""
-        if self.geometry != "auto" or self.ncells == 0:
-            return
-        torch = _torch()
-        from . import precompute as pre
+        """Order the cells for the launches of a stage and build the launch ranges.
 
-        affine, Gc, detJc = pre.compress_geometry(self.G, detJ, self._weights)
-        # rectilinear = affine with a diagonal Gc (off-diagonal factors at rounding-noise level)
-        w1 = self._tensor_weights()
-        tol = 2048.0 * float(np.finfo(self.dtype).eps)
-        diag = Gc[:, [0, 3, 5]].abs().amax(dim=1)
-        off = Gc[:, [1, 2, 4]].abs().amax(dim=1)
-        rect = (affine > 0) & (off <= tol * diag) if w1 is not None else torch.zeros_like(affine, dtype=torch.bool)
-        kind = torch.where(rect, 0, torch.where(affine > 0, 1, 2)).to(torch.int32)  # 0 rect, 1 affine, 2 streamed
-        na = int((kind < 2).sum().item())
-        nr = int((kind == 0).sum().item())
+        geometry='auto' classifies the cells (rectilinear / affine / streamed G); the peer-memory
+        halo splits them into interior and interface cells (those with a ghost dof).  Cells are
+        sorted by (interface, kind), every per-cell array follows (``cell_arrays``: attribute
+        names of (Nc,) / (Nc, n^3) tensors; the dofmap, G and detJ are handled here), G / detJ
+        are kept for the streamed cells only.  Summation order inside the atomics aside, a cell
+        permutation does not change the result."""
+        torch = _torch()
         nc = self.ncells
-        self.naff, self.nrect = na, nr
-        if nr:
-            D = self._dphi_host.astype(np.float64)
-            k1 = np.ascontiguousarray((D.T * w1[None, :]) @ D, dtype=self.dtype)  # K1 = D^T diag(w1) D
-            self._rect_tables = (k1, np.ascontiguousarray(w1, dtype=self.dtype))
-        if na == 0:
+        if nc == 0:
             return
-        if not (nr in (0, nc) and na in (0, nc)):
-            perm = torch.argsort(kind, stable=True)  # rectilinear, affine, streamed; original order kept inside
+        kind = torch.full((nc,), 2, dtype=torch.int32, device="cuda")
+        Gc = detJc = None
+        if self.geometry == "auto":
+            from . import precompute as pre
+
+            affine, Gc, detJc = pre.compress_geometry(self.G, detJ, self._weights)
+            # rectilinear = affine with a diagonal Gc (off-diagonal factors at rounding-noise level)
+            w1 = self._tensor_weights()
+            tol = 2048.0 * float(np.finfo(self.dtype).eps)
+            diag = Gc[:, [0, 3, 5]].abs().amax(dim=1)
+            off = Gc[:, [1, 2, 4]].abs().amax(dim=1)
+            rect = (affine > 0) & (off <= tol * diag) if w1 is not None else torch.zeros_like(affine, dtype=torch.bool)
+            kind = torch.where(rect, 0, torch.where(affine > 0, 1, 2)).to(torch.int32)
+            self.naff = int((kind < 2).sum().item())
+            self.nrect = int((kind == 0).sum().item())
+            if self.nrect:
+                D = self._dphi_host.astype(np.float64)
+                k1 = np.ascontiguousarray((D.T * w1[None, :]) @ D, dtype=self.dtype)  # K1 = D^T diag(w1) D
+                self._rect_tables = (k1, np.ascontiguousarray(w1, dtype=self.dtype))
+        split = self.p2p and self.split_cells
+        if split:
+            iface = (self.dofmap >= self.halo.N).any(dim=1)
+            self.ninterface = int(iface.sum().item())
+        else:
+            iface = torch.zeros(nc, dtype=torch.bool, device="cuda")
+        key = iface.to(torch.int32) * 3 + kind
+        counts = torch.bincount(key, minlength=6).cpu().tolist()
+        if not bool((key[1:] >= key[:-1]).all().item()):
+            perm = torch.argsort(key, stable=True)  # original order kept inside every range
             self.cell_perm = perm
             self.dofmap = self.dofmap[perm].contiguous()
             for name in cell_arrays:
                 setattr(self, name, getattr(self, name)[perm].contiguous())
-            Gc, detJc = Gc[perm], detJc[perm]
-            rest = perm[na:]
-            if na < nc:
-                self.G = self.G[rest].contiguous()
-                if detJ is not None:
-                    self.detJ = detJ[rest].contiguous()
-        if na == nc:
-            self.G = None  # nothing left to stream (the caller's tensor is not touched)
+            if Gc is not None:
+                Gc, detJc = Gc[perm], detJc[perm]
+            rows = perm[key[perm] % 3 == 2] if self.naff else perm
+            self.G = self.G[rows].contiguous() if rows.numel() else None
             if detJ is not None:
-                self.detJ = None
-        self.Gc = Gc[:na].contiguous()
-        self.detJc = detJc[:na].contiguous() if detJ is not None else None
+                self.detJ = detJ[rows].contiguous() if rows.numel() else None
+        elif self.naff:  # already ordered (e.g. every cell affine): drop the rows nothing streams
+            rows = torch.nonzero(kind == 2).reshape(-1)
+            self.G = self.G[rows].contiguous() if rows.numel() else None  # (the caller's tensor is not touched)
+            if detJ is not None:
+                self.detJ = detJ[rows].contiguous() if rows.numel() else None
+        if self.naff:
+            self.Gc = Gc.contiguous()
+            self.detJc = detJc.contiguous() if detJ is not None else None
+        # launch ranges
+        segs, c0, g0 = {0: [], 1: []}, 0, 0
+        for ph in (0, 1):
+            for k in (0, 1, 2):
+                n = counts[ph * 3 + k]
+                if n:
+                    segs[ph].append(Seg(k, c0, n, g0))
+                c0 += n
+                if k == 2:
+                    g0 += n
+        self._phases = {"all": segs[0] + segs[1]}
+        if split:
+            self._phases["interior"], self._phases["interface"] = segs[0], segs[1]
 
     # ---- stage pieces --------------------------------------------------------
     def _probed(self, launch):
@@ -302,50 +357,74 @@ class _RK4:
             self.halo.barrier()  # nobody's first put may land before this rank is set up
         self._opened = True
 
-    def _zero_ghosts(self):
-        """Peer-memory halo: the close kernel covers the owned entries only, so the
-        ghost part of the accumulators (b, and m for Westervelt) is cleared here."""
-        ng = self.ndofs - self.nupd
-        if ng > 0:
-            off = self.nupd * self.dtype.itemsize
-            check(fn("fus_fill", self.dtype)(0.0, self.b.data_ptr() + off, ng, current_stream()), "fus_fill")
-            if self._m_accum:
-                check(fn("fus_fill", self.dtype)(0.0, self.m.data_ptr() + off, ng, current_stream()), "fus_fill")
-
-    def _assemble(self, stage, g, dg, use_table, x, vn):  # pragma: no cover - abstract
+    def _assemble(self, stage, g, dg, use_table, x, vn, phase="all"):  # pragma: no cover - abstract
         raise NotImplementedError
 
-    def _close(self, stage, dt, count_step, base, acc):  # pragma: no cover - abstract
+    def _close(self, stage, dt, count_step, base, acc, skip=None):  # pragma: no cover - abstract
         raise NotImplementedError
 
-    def _halo_forward(self, x, vn):
-        if self.halo is not None:
-            self.halo.forward(x, vn)
+    def _close_shared(self, stage, dt, base, acc):  # pragma: no cover - abstract
+        raise NotImplementedError
 
-    def _halo_reverse(self):
-        if self.halo is not None:
-            if self._m_accum:
-                self.halo.reverse(self.b, self.m)
-            else:
-                self.halo.reverse(self.b)
+    def _sptr(self, t, row):
+        """Device address of row ``row`` of a per-cell tensor (no view objects on the launch path)."""
+        return t.data_ptr() + int(row) * t.stride(0) * t.element_size()
 
     def _enqueue_step(self, dt, t, use_table, parity=None):
         """The launches of one RK4 step whose base state is ``_uv[parity]`` (default: the current
         one); the new state is left in ``_uv[1 - parity]``.  Does not flip ``_parity``."""
         parity = self._parity if parity is None else parity
         base, acc = self._uv[parity], self._uv[1 - parity]
+        if self.p2p:
+            return self._enqueue_step_p2p(dt, t, use_table, base, acc)
         for i in range(4):
             g = dg = 0.0
             if not use_table and self.source is not None:
                 g, dg = self.source(t + C_RUNGE[i] * dt if self.source_at_stage_time else t)
             # stage input: the base state itself in stage 0 (a_0 = 0), un / vn (= ku) afterwards
             x, vn = base if i == 0 else (self.un, self.ku)
-            self._halo_forward(x, vn)
+            if self.halo is not None:
+                self.halo.forward(x, vn)
             self._assemble(i, g, dg, use_table, x, vn)
-            self._halo_reverse()
+            self._boundary(i, g, dg, use_table, vn)
+            if self.halo is not None:
+                if self._m_accum:
+                    self.halo.reverse(self.b, self.m)
+                else:
+                    self.halo.reverse(self.b)
             self._close(i, dt, use_table, base, acc)
-            if self.p2p:
-                self._zero_ghosts()
+
+    def _enqueue_step_p2p(self, dt, t, use_table, base, acc):
+        """One RK4 step with the peer-memory halo overlapped with compute (module docstring).
+        Ordering across GPUs: every wait depends only on signals the neighbours raise from
+        kernels that are stream-ordered after kernels of EARLIER phases of this rank, so the
+        step can be captured and replayed as a graph without deadlock; the FWD epoch of stage
+        i+1 is raised after the neighbour's get_add of stage i, so it also frees the ghost
+        accumulators for clearing (see csrc/halo.cu)."""
+        h = self.halo
+        accum = (self.b, self.m) if self._m_accum else (self.b,)
+        interior = "interior" if "interior" in self._phases else None
+        h.put(*base)  # stage-0 input -> the neighbours' ghost slots
+        for i in range(4):
+            g = dg = 0.0
+            if not use_table and self.source is not None:
+                g, dg = self.source(t + C_RUNGE[i] * dt if self.source_at_stage_time else t)
+            x, vn = base if i == 0 else (self.un, self.ku)
+            h.fork()
+            with h.side():
+                h.wait_forward(*accum)  # ghost values of (x, vn) have landed; ghost sums cleared
+            if interior:
+                self._assemble(i, g, dg, use_table, x, vn, "interior")
+            h.join()
+            self._assemble(i, g, dg, use_table, x, vn, "interface" if interior else "all")
+            self._boundary(i, g, dg, use_table, vn)
+            h.signal_reverse()
+            h.fork()
+            with h.side():
+                h.get_add(*accum)
+                self._close_shared(i, dt, base, acc)  # + put of the next stage input (not after the last stage)
+            self._close(i, dt, use_table, base, acc, skip=h.shared_mask)
+            h.join()
 
     def _close_args(self, stage, dt, base, acc):
         """(u, v, u0, v0 pointers, bdt, adt_next, next_mode) of the close kernel for ``stage``:
@@ -393,7 +472,7 @@ class _RK4:
             if self._graph_dt != dt or self._graph_tab != self.gtab.data_ptr():
                 self._capture(dt)
             for _ in range(nsteps):
-                self.replay_step(dt)
+                self._replay_step(dt)
         else:
             for k in range(nsteps):
                 self._enqueue_step(dt, 0.0, True)
@@ -424,10 +503,15 @@ class _RK4:
         self.nstep += 1
         return self.t
 
-    def replay_step(self, dt):
+    def _replay_step(self, dt):
         """One RK4 step reading the source table row ``step_dev`` points at: a
-        graph replay (or, when capture is unavailable, the same launches eagerly)."""
+        graph replay (or, when capture is unavailable, the same launches eagerly).
+        Private: the caller (``rk4``, or a benchmark that rewrites the one-row table itself)
+        is responsible for ``step_dev`` staying inside the loaded table; the step size is
+        baked into the captured graph."""
         if self._graph is not None:
+            if dt != self._graph_dt:
+                raise _lib.FusError(f"_replay_step: the graph was captured with dt = {self._graph_dt}, got {dt}")
             self._graph[self._parity].replay()
         else:
             self._enqueue_step(dt, 0.0, True)
@@ -490,9 +574,10 @@ class LinearSpectral3D(_RK4):
     def __init__(self, P, float_type, ndofs, dofmap, G, detJ, dphi_1D, cell_coeff1, cell_coeff2,
                  bfacet_dofmap1=None, detJ_f1=None, facet_coeff1=None, bfacet_dofmap2=None,
                  detJ_f2=None, facet_coeff2=None, halo=None, source=None,
-                 source_at_stage_time=True, use_graph=True, geometry="stream", weights=None):
+                 source_at_stage_time=True, use_graph=True, geometry="stream", weights=None,
+                 split_cells=True):
         super().__init__(P, float_type, ndofs, dofmap, G, dphi_1D, halo, source,
-                         source_at_stage_time, use_graph, geometry, weights)
+                         source_at_stage_time, use_graph, geometry, weights, split_cells)
         torch = _torch()
         self.cell_coeff2 = _dev(cell_coeff2, self.T)
         c1 = _dev(cell_coeff1, self.T)
@@ -513,36 +598,41 @@ class LinearSpectral3D(_RK4):
         self._boundary_setup(terms)
         self._setup_geometry(None, ["cell_coeff2"])
 
-    def _stiffness(self, x=None):
+    def _stiffness(self, x=None, phase="all"):
         x = self.un if x is None else x
-        nr, na, nc, st = self.nrect, self.naff, self.ncells, current_stream()
-        if nr:  # rectilinear cells: three decoupled 1-D stiffness products
-            check(fn("fus_stiffness_rect", self.dtype)(
-                x.data_ptr(), self.cell_coeff2.data_ptr(), self.b.data_ptr(), self.Gc.data_ptr(),
-                self.dofmap.data_ptr(), None, nr, self.P, FUS_TABLES_RESIDENT, st), "fus_stiffness_rect")
-        if na > nr:  # affine cells: 6 factors per cell, nothing streamed but the dofmap
-            check(fn("fus_stiffness_affine", self.dtype)(
-                x.data_ptr(), self.cell_coeff2[nr:].data_ptr(), self.b.data_ptr(), self.Gc[nr:].data_ptr(),
-                self._weights.data_ptr(), self.dofmap[nr:].data_ptr(), None, na - nr, self.P,
-                FUS_TABLES_RESIDENT, st), "fus_stiffness_affine")
-        if na < nc:
-            check(fn("fus_stiffness", self.dtype)(
-                x.data_ptr(), self.cell_coeff2[na:].data_ptr(), self.b.data_ptr(), self.G.data_ptr(),
-                self.dofmap[na:].data_ptr(), None, nc - na, self.P, FUS_TABLES_RESIDENT, st),
-                "fus_stiffness")
+        st, xp, bp, sp = current_stream(), x.data_ptr(), self.b.data_ptr(), self._sptr
+        for sg in self._phases[phase]:
+            cf, dm = sp(self.cell_coeff2, sg.c0), sp(self.dofmap, sg.c0)
+            if sg.kind == 0:  # rectilinear cells: three decoupled 1-D stiffness products
+                check(fn("fus_stiffness_rect", self.dtype)(
+                    xp, cf, bp, sp(self.Gc, sg.c0), dm, None, sg.n, self.P, FUS_TABLES_RESIDENT, st),
+                    "fus_stiffness_rect")
+            elif sg.kind == 1:  # affine cells: 6 factors per cell, nothing streamed but the dofmap
+                check(fn("fus_stiffness_affine", self.dtype)(
+                    xp, cf, bp, sp(self.Gc, sg.c0), self._weights.data_ptr(), dm, None, sg.n, self.P,
+                    FUS_TABLES_RESIDENT, st), "fus_stiffness_affine")
+            else:
+                check(fn("fus_stiffness", self.dtype)(
+                    xp, cf, bp, sp(self.G, sg.g0), dm, None, sg.n, self.P, FUS_TABLES_RESIDENT, st),
+                    "fus_stiffness")
 
-    def _assemble(self, stage, g, dg, use_table, x, vn):
+    def _assemble(self, stage, g, dg, use_table, x, vn, phase="all"):
         # b += K(-1/rho; un)                                  (cuda/demo_linear_box.py:543-545)
-        self._probed(lambda: self._stiffness(x))
-        # b += g * src + vn * absb                            (:546-551)
-        self._boundary(stage, g, dg, use_table, vn)
+        self._probed(lambda: self._stiffness(x, phase))
 
-    def _close(self, stage, dt, count_step, base, acc):
+    def _close(self, stage, dt, count_step, base, acc, skip=None):
         u, v, u0, v0, bdt, adt, mode = self._close_args(stage, dt, base, acc)
         check(fn("fus_rk_close", self.dtype)(
             u, v, u0, v0, self.ku.data_ptr(), None, self.un.data_ptr(), self.b.data_ptr(), self.m.data_ptr(),
-            bdt, adt, mode, self.nupd, self.step_dev.data_ptr() if count_step else None, current_stream()),
+            bdt, adt, mode, self.nupd, self.step_dev.data_ptr() if count_step else None, skip, current_stream()),
             "fus_rk_close")
+
+    def _close_shared(self, stage, dt, base, acc):
+        u, v, u0, v0, bdt, adt, mode = self._close_args(stage, dt, base, acc)
+        check(fn("fus_rk_close_shared", self.dtype)(
+            self.halo.handle, 0, int(stage < 3), u, v, u0, v0, self.ku.data_ptr(), self.un.data_ptr(),
+            self.b.data_ptr(), self.m.data_ptr(), None, None, None, bdt, adt, mode, current_stream()),
+            "fus_rk_close_shared")
 
 
 class WesterveltSpectral3D(_RK4):
@@ -571,9 +661,9 @@ class WesterveltSpectral3D(_RK4):
                  facet_coeff1_1=None, facet_coeff2_1=None, bfacet_dofmap2=None, detJ_f2=None,
                  facet_coeff1_2=None, facet_coeff2_2=None, halo=None, source=None,
                  source_at_stage_time=True, use_graph=True, geometry="stream", weights=None,
-                 mass_form="pointwise"):
+                 mass_form="pointwise", split_cells=True):
         super().__init__(P, float_type, ndofs, dofmap, G, dphi_1D, halo, source,
-                         source_at_stage_time, use_graph, geometry, weights)
+                         source_at_stage_time, use_graph, geometry, weights, split_cells)
         torch = _torch()
         if mass_form not in ("pointwise", "cells"):
             raise ValueError("mass_form must be 'pointwise' or 'cells'")
@@ -618,67 +708,67 @@ class WesterveltSpectral3D(_RK4):
     def _state(self):
         return super()._state() + [self.m0]
 
-    def _assemble(self, stage, g, dg, use_table, x, vn):
-        # b += K(c3; un) + K(c4; vn) + M(c5; vn^2) and m += M(c2; un): ONE pass over G, detJ
+    def _assemble(self, stage, g, dg, use_table, x, vn, phase="all"):
+        # b += K(c3; un) + K(c4; vn) [+ M(c5; vn^2) and m += M(c2; un)]: ONE pass over G (, detJ)
         # and the dofmap, un / vn gathered once                    (:609-612, :620-628)
-        self._probed(lambda: self._stage_kernel(x, vn))
-        # b += g*src + dg*src2 + vn*absb                                      (:629-639)
-        self._boundary(stage, g, dg, use_table, vn)
+        self._probed(lambda: self._stage_kernel(x, vn, phase))
 
-    def _stage_kernel(self, x=None, vn=None):
+    def _stage_kernel(self, x=None, vn=None, phase="all"):
         x = self.un if x is None else x
         vn = self.ku if vn is None else vn
-        nr, na, nc, st = self.nrect, self.naff, self.ncells, current_stream()
-        if not self._m_accum:
-            # b += K(c3; un) + K(c4; vn): the dual stiffness action, one pass over G
-            if nr:
-                check(fn("fus_stiffness2_rect", self.dtype)(
-                    x.data_ptr(), self.c3.data_ptr(), vn.data_ptr(), self.c4.data_ptr(), self.b.data_ptr(),
-                    self.Gc.data_ptr(), self.dofmap.data_ptr(), None, nr, self.P, FUS_TABLES_RESIDENT, st),
-                    "fus_stiffness2_rect")
-            if na > nr:
-                check(fn("fus_stiffness2_affine", self.dtype)(
-                    x.data_ptr(), self.c3[nr:].data_ptr(), vn.data_ptr(), self.c4[nr:].data_ptr(), self.b.data_ptr(),
-                    self.Gc[nr:].data_ptr(), self._weights.data_ptr(), self.dofmap[nr:].data_ptr(), None, na - nr,
-                    self.P, FUS_TABLES_RESIDENT, st), "fus_stiffness2_affine")
-            if na < nc:
-                check(fn("fus_stiffness2", self.dtype)(
-                    x.data_ptr(), self.c3[na:].data_ptr(), vn.data_ptr(), self.c4[na:].data_ptr(), self.b.data_ptr(),
-                    self.G.data_ptr(), self.dofmap[na:].data_ptr(), None, nc - na, self.P, FUS_TABLES_RESIDENT, st),
-                    "fus_stiffness2")
-            return
-        if nr:
-            check(fn("fus_stiffness_westervelt_rect", self.dtype)(
-                x.data_ptr(), self.c3.data_ptr(), vn.data_ptr(), self.c4.data_ptr(),
-                self.c2.data_ptr(), self.c5.data_ptr(), self.m.data_ptr(), self.b.data_ptr(),
-                self.Gc.data_ptr(), self.detJc.data_ptr(), self.dofmap.data_ptr(), None, nr, self.P,
-                FUS_TABLES_RESIDENT, st), "fus_stiffness_westervelt_rect")
-        if na > nr:
-            check(fn("fus_stiffness_westervelt_affine", self.dtype)(
-                x.data_ptr(), self.c3[nr:].data_ptr(), vn.data_ptr(), self.c4[nr:].data_ptr(),
-                self.c2[nr:].data_ptr(), self.c5[nr:].data_ptr(), self.m.data_ptr(), self.b.data_ptr(),
-                self.Gc[nr:].data_ptr(), self.detJc[nr:].data_ptr(), self._weights.data_ptr(),
-                self.dofmap[nr:].data_ptr(), None, na - nr, self.P, FUS_TABLES_RESIDENT, st),
-                "fus_stiffness_westervelt_affine")
-        if na < nc:
-            check(fn("fus_stiffness_westervelt", self.dtype)(
-                x.data_ptr(), self.c3[na:].data_ptr(), vn.data_ptr(), self.c4[na:].data_ptr(),
-                self.c2[na:].data_ptr(), self.c5[na:].data_ptr(), self.m.data_ptr(), self.b.data_ptr(),
-                self.G.data_ptr(), self.detJ.data_ptr(), self.dofmap[na:].data_ptr(), None, nc - na, self.P,
-                FUS_TABLES_RESIDENT, st), "fus_stiffness_westervelt")
+        st, sp, P, R = current_stream(), self._sptr, self.P, FUS_TABLES_RESIDENT
+        xp, vp, bp = x.data_ptr(), vn.data_ptr(), self.b.data_ptr()
+        for sg in self._phases[phase]:
+            c0 = sg.c0
+            c3, c4, dm = sp(self.c3, c0), sp(self.c4, c0), sp(self.dofmap, c0)
+            if not self._m_accum:
+                # b += K(c3; un) + K(c4; vn): the dual stiffness action, one pass over G
+                if sg.kind == 0:
+                    check(fn("fus_stiffness2_rect", self.dtype)(
+                        xp, c3, vp, c4, bp, sp(self.Gc, c0), dm, None, sg.n, P, R, st), "fus_stiffness2_rect")
+                elif sg.kind == 1:
+                    check(fn("fus_stiffness2_affine", self.dtype)(
+                        xp, c3, vp, c4, bp, sp(self.Gc, c0), self._weights.data_ptr(), dm, None, sg.n, P, R, st),
+                        "fus_stiffness2_affine")
+                else:
+                    check(fn("fus_stiffness2", self.dtype)(
+                        xp, c3, vp, c4, bp, sp(self.G, sg.g0), dm, None, sg.n, P, R, st), "fus_stiffness2")
+                continue
+            c2, c5, mp = sp(self.c2, c0), sp(self.c5, c0), self.m.data_ptr()
+            if sg.kind == 0:
+                check(fn("fus_stiffness_westervelt_rect", self.dtype)(
+                    xp, c3, vp, c4, c2, c5, mp, bp, sp(self.Gc, c0), sp(self.detJc, c0), dm, None, sg.n, P, R, st),
+                    "fus_stiffness_westervelt_rect")
+            elif sg.kind == 1:
+                check(fn("fus_stiffness_westervelt_affine", self.dtype)(
+                    xp, c3, vp, c4, c2, c5, mp, bp, sp(self.Gc, c0), sp(self.detJc, c0),
+                    self._weights.data_ptr(), dm, None, sg.n, P, R, st), "fus_stiffness_westervelt_affine")
+            else:
+                check(fn("fus_stiffness_westervelt", self.dtype)(
+                    xp, c3, vp, c4, c2, c5, mp, bp, sp(self.G, sg.g0), sp(self.detJ, sg.g0), dm, None, sg.n,
+                    P, R, st), "fus_stiffness_westervelt")
 
-    def _close(self, stage, dt, count_step, base, acc):
+    def _close(self, stage, dt, count_step, base, acc, skip=None):
         u, v, u0, v0, bdt, adt, mode = self._close_args(stage, dt, base, acc)
+        step = self.step_dev.data_ptr() if count_step else None
         if not self._m_accum:
             check(fn("fus_rk_close_westervelt_pw", self.dtype)(
                 u, v, u0, v0, self.ku.data_ptr(), None, self.un.data_ptr(), self.b.data_ptr(), self.m0.data_ptr(),
-                self.m2.data_ptr(), self.m5.data_ptr(), bdt, adt, mode, self.nupd,
-                self.step_dev.data_ptr() if count_step else None, current_stream()), "fus_rk_close_westervelt_pw")
+                self.m2.data_ptr(), self.m5.data_ptr(), bdt, adt, mode, self.nupd, step, skip, current_stream()),
+                "fus_rk_close_westervelt_pw")
             return
         check(fn("fus_rk_close_westervelt", self.dtype)(
             u, v, u0, v0, self.ku.data_ptr(), None, self.un.data_ptr(), self.b.data_ptr(), self.m.data_ptr(),
-            self.m0.data_ptr(), bdt, adt, mode, self.nupd, self.step_dev.data_ptr() if count_step else None,
-            current_stream()), "fus_rk_close_westervelt")
+            self.m0.data_ptr(), bdt, adt, mode, self.nupd, step, skip, current_stream()), "fus_rk_close_westervelt")
+
+    def _close_shared(self, stage, dt, base, acc):
+        u, v, u0, v0, bdt, adt, mode = self._close_args(stage, dt, base, acc)
+        pw = not self._m_accum
+        check(fn("fus_rk_close_shared", self.dtype)(
+            self.halo.handle, 2 if pw else 1, int(stage < 3), u, v, u0, v0, self.ku.data_ptr(), self.un.data_ptr(),
+            self.b.data_ptr(), None if pw else self.m.data_ptr(), self.m0.data_ptr(),
+            self.m2.data_ptr() if pw else None, self.m5.data_ptr() if pw else None, bdt, adt, mode,
+            current_stream()), "fus_rk_close_shared")
 
     def stage_bytes(self):
         s = self.dtype.itemsize

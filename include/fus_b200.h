@@ -30,15 +30,17 @@
 extern "C" {
 #endif
 
-#define FUS_ABI_VERSION 1
+#define FUS_ABI_VERSION 2
 
 /* error codes outside the cudaError_t range */
 #define FUS_ERR_BAD_DEGREE 100001
 #define FUS_ERR_BAD_ARGUMENT 100002
+#define FUS_ERR_HALO_TIMEOUT 100003
 
 /* flags for fus_stiffness* */
 #define FUS_TABLES_RESIDENT 1 /* dphi for this (P, type) already uploaded: skip the table copy */
 #define FUS_NO_ATOMICS 2      /* caller guarantees no two cells of this launch share a dof (colouring) */
+#define FUS_HOST_Y_ZERO 4     /* fus_stiffness_host_*: y_host holds zeros - skip its upload, clear y on the device */
 
 int fus_abi_version(void);
 const char* fus_last_error(void);
@@ -229,27 +231,82 @@ int fus_unpack_multi_f64(const double* in, double* const* out, int nvec, const i
 int fus_unpack_multi_f32(const float* in, float* const* out, int nvec, const int64_t* index,
                          int64_t n, int64_t offset, int add, void* stream);
 
-/* Halo exchange through NVLink peer memory - the whole of
- * cuda/scatterer.py:191-277 (forward) / :104-188 (reverse) as ONE kernel each:
- *   put     : peer_v[remote_pos[e]]  = local_v[idx[e]]     (owner -> ghost copies)
- *   get_add : local_v[idx[e]]       += peer_v[remote_pos[e]] (ghost sums -> owner)
- * e runs over the concatenated ghosts_data lists (MY owned dofs that are ghosts on
- * a neighbour); entry_seg[e] is the neighbour segment, peer[seg*nvec + v] the device
- * address of vector v in that neighbour's memory (a peer mapping), remote_pos[e]
- * the entry's position in the neighbour's vector.  `local` and `peer` are arrays
- * of nvec (<= 4) pointers: `local` in HOST memory (read at launch), `peer` in
- * DEVICE memory.  Ordering across GPUs (a barrier after put, before and after
- * get_add) is the caller's. */
-int fus_halo_put_f64(double* const* local, int nvec, const uint64_t* peer, const int64_t* idx,
-                     const int64_t* remote_pos, const int32_t* entry_seg, int64_t n, void* stream);
-int fus_halo_put_f32(float* const* local, int nvec, const uint64_t* peer, const int64_t* idx,
-                     const int64_t* remote_pos, const int32_t* entry_seg, int64_t n, void* stream);
-int fus_halo_get_add_f64(double* const* local, int nvec, const uint64_t* peer, const int64_t* idx,
-                         const int64_t* remote_pos, const int32_t* entry_seg, int64_t n,
-                         void* stream);
-int fus_halo_get_add_f32(float* const* local, int nvec, const uint64_t* peer, const int64_t* idx,
-                         const int64_t* remote_pos, const int32_t* entry_seg, int64_t n,
-                         void* stream);
+/* --------------------------------------------------------------------- *
+ * Halo exchange through NVLink peer memory - the whole of
+ * cuda/scatterer.py:104-277 (scatter_reverse / scatter_forward factories: per-neighbour
+ * pack kernel, device synchronise, host-staged MPI Isend/Irecv + Waitall, unpack kernel)
+ * behind ONE handle.  Data moves with plain loads / stores into peer-mapped memory;
+ * ordering across GPUs is per-neighbour 64-bit epoch flags (st.release.sys /
+ * ld.acquire.sys on a signal pad), issued by this library's own kernels: no host
+ * synchronisation, no global barrier, capturable in a CUDA graph.
+ *
+ * The caller provides peer-addressable memory (CUDA VMM / cudaIpc mappings; the Python
+ * layer uses torch's symmetric-memory allocator for the allocation and rendezvous only):
+ * every exchanged vector must sit at the SAME byte offset of a symmetric arena on every
+ * rank, so that its address on rank q is `local address + peer_delta[q]`.
+ * --------------------------------------------------------------------- */
+typedef struct fus_halo fus_halo_t;
+
+typedef struct {
+  int32_t rank, world;        /* flag slots are indexed by global rank                               */
+  int32_t n_ghost_ranks;      /* neighbours holding ghost copies of dofs I own (ghosts_data[2])      */
+  const int32_t* ghost_ranks; /* HOST [n_ghost_ranks]                                                */
+  int32_t n_owner_ranks;      /* neighbours owning my ghosts (owners_data[2], cuda/utils.py:30-41)   */
+  const int32_t* owner_ranks; /* HOST [n_owner_ranks]                                                */
+  int64_t n;                  /* shared entries: ghosts_data index lists concatenated (utils.py:57-73) */
+  const int64_t* idx;         /* HOST [n] local (owned) index of the entry                           */
+  const int64_t* remote_pos;  /* HOST [n] index of the same dof in that neighbour's vector           */
+  const int32_t* entry_seg;   /* HOST [n] position of the neighbour in ghost_ranks                   */
+  int64_t size_local;         /* owned dofs: vectors are [owned | ghosts]                            */
+  int64_t num_ghosts;
+  void* signal_pad;           /* DEVICE my pad, fus_halo_pad_bytes(world) bytes, zeroed, peer-mapped */
+  const uint64_t* peer_pad;   /* HOST [world] device address of rank q's pad as mapped HERE (0: unmapped) */
+  const int64_t* peer_delta;  /* HOST [world] (rank q's arena base as mapped here) - (my arena base), bytes */
+} fus_halo_desc_t;
+
+int64_t fus_halo_pad_bytes(int world);
+/* Builds the device tables (one cudaMalloc owned by the handle, like the per-neighbour
+ * buffers the reference's factories own: cuda/scatterer.py:133-138).  Host arrays of
+ * `desc` are copied.  Collective only in the sense that every rank must create its own. */
+int fus_halo_create(const fus_halo_desc_t* desc, fus_halo_t** out);
+int fus_halo_destroy(fus_halo_t* h);
+/* unique owned dofs that are ghosts somewhere, and the bitmask over [0, size_local)
+ * (bit d%8 of byte d/8) that fus_rk_close_* takes as skip_mask (DEVICE pointer). */
+int64_t fus_halo_num_shared(const fus_halo_t* h);
+const uint8_t* fus_halo_shared_mask(const fus_halo_t* h);
+/* 0, or FUS_ERR_HALO_TIMEOUT when a wait gave up (a neighbour never signalled). Synchronous. */
+int fus_halo_status(fus_halo_t* h);
+
+/* Stand-alone exchanges of up to 4 vectors (HOST array of DEVICE pointers), safe in any
+ * call sequence that every rank makes identically:
+ *   forward = scatter_forward(...)(buffer), cuda/scatterer.py:191-277: owner -> ghost overwrite
+ *   reverse = scatter_reverse(...)(buffer), cuda/scatterer.py:104-188: ghost sums added into the
+ *             owner; the ghost region keeps its values.
+ * Asynchronous on `stream` (the reference synchronises the device: scatterer.py:186, 275). */
+int fus_halo_forward_f64(fus_halo_t* h, double* const* vecs, int nvec, void* stream);
+int fus_halo_forward_f32(fus_halo_t* h, float* const* vecs, int nvec, void* stream);
+int fus_halo_reverse_f64(fus_halo_t* h, double* const* vecs, int nvec, void* stream);
+int fus_halo_reverse_f32(fus_halo_t* h, float* const* vecs, int nvec, void* stream);
+
+/* Split-phase pieces for a time-stepping loop that overlaps the exchange with compute
+ * (used by the fused solvers; the ordering argument is in csrc/halo.cu):
+ *   put          : owner values -> the neighbours' ghost slots, then the FWD epoch
+ *   wait_forward : wait for the FWD epoch of every owner of my ghosts; then (nzero > 0) clear
+ *                  the ghost part [size_local, size_local + num_ghosts) of `zero_vecs`
+ *   signal_reverse : REV epoch -> every owner of my ghosts ("my partial sums are complete")
+ *   get_add      : wait for the REV epoch of every ghosting neighbour, then
+ *                  v[idx[e]] += peer_v[remote_pos[e]]
+ *   barrier      : neighbour barrier
+ * Every put must be matched by one wait_forward on the neighbours, every signal_reverse by
+ * one get_add. */
+int fus_halo_put_f64(fus_halo_t* h, double* const* vecs, int nvec, void* stream);
+int fus_halo_put_f32(fus_halo_t* h, float* const* vecs, int nvec, void* stream);
+int fus_halo_wait_forward_f64(fus_halo_t* h, double* const* zero_vecs, int nzero, void* stream);
+int fus_halo_wait_forward_f32(fus_halo_t* h, float* const* zero_vecs, int nzero, void* stream);
+int fus_halo_signal_reverse(fus_halo_t* h, void* stream);
+int fus_halo_get_add_f64(fus_halo_t* h, double* const* vecs, int nvec, void* stream);
+int fus_halo_get_add_f32(fus_halo_t* h, float* const* vecs, int nvec, void* stream);
+int fus_halo_barrier(fus_halo_t* h, void* stream);
 
 /* --------------------------------------------------------------------- *
  * Fused RK4 stage kernels.  Replace the 13 vector launches per stage of
@@ -284,13 +341,35 @@ int fus_rk_open_f32(const float* u, const float* v, float* u0, float* v0, float*
  * kv is stored when non-NULL; it may be NULL in modes 1-4 (nothing reads
  * it again).  step_dev (may be NULL) is a device step counter incremented in
  * modes 2 and 4 - it indexes the source table of fus_boundary_terms, so a whole RK
- * step can be replayed as a CUDA graph with no host work. */
+ * step can be replayed as a CUDA graph with no host work.
+ * skip_mask (DEVICE, may be NULL): bit d%8 of byte d/8 set => dof d is left untouched here
+ * (multi-GPU: the shared dofs, closed by fus_rk_close_shared_* after the reverse halo). */
 int fus_rk_close_f64(double* u, double* v, double* u0, double* v0, double* ku, double* kv,
                      double* un, double* b, const double* m, double bdt, double adt_next,
-                     int next_mode, int64_t n, int64_t* step_dev, void* stream);
+                     int next_mode, int64_t n, int64_t* step_dev, const uint8_t* skip_mask,
+                     void* stream);
 int fus_rk_close_f32(float* u, float* v, float* u0, float* v0, float* ku, float* kv, float* un,
                      float* b, const float* m, float bdt, float adt_next, int next_mode,
-                     int64_t n, int64_t* step_dev, void* stream);
+                     int64_t n, int64_t* step_dev, const uint8_t* skip_mask, void* stream);
+
+/* Multi-GPU stage closing on the unique owned dofs that are ghosts on a neighbour - the dofs
+ * fus_rk_close_* leaves out when given skip_mask = fus_halo_shared_mask(halo): their b is complete
+ * only once the reverse halo has landed, so the bulk of the vector is closed while that exchange is
+ * in flight and this (small, indexed) kernel runs after fus_halo_get_add.  With put_next != 0 it is
+ * fused with the forward halo of the NEXT stage: the fresh stage input (un, ku; or u, v in
+ * next_mode 4) is stored straight into the neighbours' ghost slots, followed by the FWD epoch
+ * (= fus_halo_put of those two vectors).  variant 0: fus_rk_close (m); 1: fus_rk_close_westervelt
+ * (m, m0); 2: fus_rk_close_westervelt_pw (m0, m2, m5); unused mass pointers may be NULL.
+ * Replaces scatter_reverse(b) -> pointwise_divide/axpy -> (next stage) scatter_forward(un),
+ * scatter_forward(vn) of cuda/demo_linear_box.py:536-563. */
+int fus_rk_close_shared_f64(fus_halo_t* halo, int variant, int put_next, double* u, double* v,
+                            double* u0, double* v0, double* ku, double* un, double* b, double* m,
+                            const double* m0, const double* m2, const double* m5, double bdt,
+                            double adt_next, int next_mode, void* stream);
+int fus_rk_close_shared_f32(fus_halo_t* halo, int variant, int put_next, float* u, float* v,
+                            float* u0, float* v0, float* ku, float* un, float* b, float* m,
+                            const float* m0, const float* m2, const float* m5, float bdt,
+                            float adt_next, int next_mode, void* stream);
 
 /* Boundary-facet terms of one stage through precomputed diagonals on a compact
  * list of UNIQUE dofs: b[dof[i]] += g * src[i] + dg * src2[i] + vn[dof[i]] * absb[i].
@@ -325,11 +404,11 @@ int fus_westervelt_mass_f32(const float* un, const float* vn, const float* c2, c
 int fus_rk_close_westervelt_f64(double* u, double* v, double* u0, double* v0, double* ku,
                                 double* kv, double* un, double* b, double* m, const double* m0,
                                 double bdt, double adt_next, int next_mode, int64_t n,
-                                int64_t* step_dev, void* stream);
+                                int64_t* step_dev, const uint8_t* skip_mask, void* stream);
 int fus_rk_close_westervelt_f32(float* u, float* v, float* u0, float* v0, float* ku, float* kv,
                                 float* un, float* b, float* m, const float* m0, float bdt,
                                 float adt_next, int next_mode, int64_t n, int64_t* step_dev,
-                                void* stream);
+                                const uint8_t* skip_mask, void* stream);
 
 /* Pointwise form of the Westervelt stage closing.  The lumped mass is diagonal, so the cell-mass
  * pair of cuda/demo_nonlinear_bowl.py:609-612, 626-628 needs no pass over the cells:
@@ -341,11 +420,12 @@ int fus_rk_close_westervelt_pw_f64(double* u, double* v, double* u0, double* v0,
                                    double* kv, double* un, double* b, const double* m0,
                                    const double* m2, const double* m5, double bdt,
                                    double adt_next, int next_mode, int64_t n, int64_t* step_dev,
-                                   void* stream);
+                                   const uint8_t* skip_mask, void* stream);
 int fus_rk_close_westervelt_pw_f32(float* u, float* v, float* u0, float* v0, float* ku, float* kv,
                                    float* un, float* b, const float* m0, const float* m2,
                                    const float* m5, float bdt, float adt_next, int next_mode,
-                                   int64_t n, int64_t* step_dev, void* stream);
+                                   int64_t n, int64_t* step_dev, const uint8_t* skip_mask,
+                                   void* stream);
 
 /* --------------------------------------------------------------------- *
  * Geometry precompute on the device - cuda/precompute.py:17-163
@@ -383,7 +463,11 @@ int fus_eval_points_f32(const float* u, const int32_t* dofmap, const int32_t* ce
  * inside the call).  x_host / y_host are HOST pointers (pinned for full
  * speed); every other pointer is a device pointer as above.
  * y_host += K x_host, staged through the caller-provided device scratch
- * x_dev / y_dev (nd each).  Synchronous on return.
+ * x_dev / y_dev (nd each).  Synchronous on return.  The cells are cut into 8 ranges; the
+ * upload of the x (and y) piece the next range needs, the action on the current range and the
+ * download of the part of y the previous range completed run concurrently on three streams
+ * (full-duplex PCIe).  With FUS_HOST_Y_ZERO (y_host holds zeros, the reference's calling
+ * pattern: cuda/time_operators.py:276-279 zero-fills b before every launch) y is not uploaded.
  * --------------------------------------------------------------------- */
 int fus_stiffness_host_f64(const double* x_host, double* y_host, int64_t nd, double* x_dev,
                            double* y_dev, const double* coeff, const double* G,

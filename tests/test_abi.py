@@ -17,7 +17,7 @@ def _declared():
 
 def test_library_loads_and_exports_header_symbols():
     lib = _lib.lib()
-    assert lib.fus_abi_version() == 1
+    assert lib.fus_abi_version() == 2
     names = _declared()
     assert len(names) > 40
     missing = [n for n in names if not hasattr(lib, n)]
