@@ -576,6 +576,7 @@ class P2PHaloExchange:
         self.nshared = int(lib.fus_halo_num_shared(h))
         self.shared_mask = lib.fus_halo_shared_mask(h)  # device address of the bitmask
         self._side = None
+        self.use_side = True  # put the exchange kernels on a second stream (False: A/B measurements)
         fabric.host_barrier()  # every rank's pad and handle exist before the first signal
 
     def __del__(self):
@@ -665,7 +666,7 @@ class P2PHaloExchange:
     # -- second stream for the exchange (real GPUs only) -----------------------------
     @property
     def concurrent(self):
-        return not self.fabric.emulated
+        return self.use_side and not self.fabric.emulated
 
     def _side_stream(self):
         import torch

@@ -185,7 +185,8 @@ def test_device_geometry_vs_reference_golden(golden_dir, P, tag):
     # device in / device out, both tables in one pass
     Gd, Jd = torch.zeros_like(d(g["G"])), torch.zeros_like(d(g["detJ"]))
     pre.compute_geometry(Gd, Jd, (d(g["x_dofs"]), d(g["x_g"])), Nc, d(g["dphi"]), d(g["wts"]))
-    assert np.array_equal(Gd.cpu().numpy(), G) and np.array_equal(Jd.cpu().numpy(), detJ)
+    assert rel_l2(Gd.cpu().numpy(), g["G"]) < tol and rel_l2(Jd.cpu().numpy(), g["detJ"]) < tol
+    assert rel_l2(Gd.cpu().numpy(), G) < (1e-14 if tag == "f64" else 1e-6)
     # a tensor of the wrong dtype is refused, not reinterpreted
     with pytest.raises(Exception):
         pre.compute_geometry(Gd, Jd, (d(g["x_dofs"]).to(torch.int64), d(g["x_g"])), Nc, d(g["dphi"]), d(g["wts"]))
@@ -359,7 +360,7 @@ def test_westervelt_f32_partitioned_p2p_vs_serial_oracle(mass_form):
             q.cell_coeff4, q.cell_coeff5, q.bfacet_dofmap1, q.detJ_f1, q.facet_coeff1_1, q.facet_coeff2_1,
             q.bfacet_dofmap2, q.detJ_f2, q.facet_coeff1_2, q.facet_coeff2_2, halo=halo,
             source=lambda t: westervelt_source(t, q.f0, q.p0, q.c0), use_graph=False, mass_form=mass_form)
-        assert s.ninterface > 0 and "interior" in s._phases
+        assert "interior" in s._phases and (r == 0 or s.ninterface > 0)  # rank 0 owns all it touches
         s.init()
         s.rk4(0.0, dt, nsteps)
         torch.cuda.synchronize()
