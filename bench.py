@@ -537,6 +537,7 @@ def main():
         torch.cuda.current_stream().synchronize()
         return float(sample_host[0])
 
+    solver.begin_steps()
     for k in range(warmup):
         e2e_step(k)
     barrier()
@@ -545,6 +546,7 @@ def main():
     for k in range(a.steps):
         e2e_step(warmup + k)
     e1.record()
+    solver.end_steps()
     barrier()
     e2e_elapsed = maxr(max(e0.elapsed_time(e1) * 1e-3, 0.0))
     e2e_wall = maxr(time.perf_counter() - t0)

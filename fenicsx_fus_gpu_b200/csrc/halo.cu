@@ -72,11 +72,18 @@ __global__ void __launch_bounds__(kThreads) halo_put_kernel(const FusHaloDev h, 
     fus_signal(&h.ctr[FUS_CTR_TICKET_PUT], &h.ctr[FUS_CTR_FWD_SENT], h.fwd_targets, h.n_ghost_ranks);
 }
 
-// wait for the FWD epoch of every owner of my ghosts; then clear v[size_local .. + num_ghosts)
+// Wait (ONE warp: a spinning grid would hold registers and thread slots that the kernels running
+// beside it - the stiffness kernel, the close kernel - need) for the epoch of every source rank in
+// flag row `row`, then advance the matching "waited" counter.
+__global__ void __launch_bounds__(32) halo_wait_kernel(const FusHaloDev h, int row, int waited_ctr, const int* src, int nsrc) {
+  const unsigned long long expect = h.ctr[waited_ctr] + 1ULL;
+  fus_wait_flags(h.pad + (long long)row * h.world, src, nsrc, expect, h.ctr);
+  if (threadIdx.x == 0) h.ctr[waited_ctr] = expect;
+}
+
+// clear v[size_local .. + num_ghosts) of up to 4 vectors
 template <typename T>
-__global__ void __launch_bounds__(kThreads) halo_wait_forward_kernel(const FusHaloDev h, const VecArgs<T> z) {
-  const unsigned long long expect = h.ctr[FUS_CTR_FWD_WAITED] + 1ULL;
-  fus_wait_flags(h.pad + (long long)FUS_ROW_FWD * h.world, h.owner_ranks, h.n_owner_ranks, expect, h.ctr);
+__global__ void __launch_bounds__(kThreads) halo_zero_ghosts_kernel(const FusHaloDev h, const VecArgs<T> z) {
   const long long stride = (long long)gridDim.x * kThreads;
 #pragma unroll
   for (int v = 0; v < kMaxVec; ++v) {
@@ -85,23 +92,16 @@ __global__ void __launch_bounds__(kThreads) halo_wait_forward_kernel(const FusHa
       for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < h.num_ghosts; i += stride) p[i] = T(0);
     }
   }
-  if (fus_last_block(&h.ctr[FUS_CTR_TICKET_WAIT]) && threadIdx.x == 0) {
-    h.ctr[FUS_CTR_FWD_WAITED] = expect;
-    h.ctr[FUS_CTR_TICKET_WAIT] = 0ULL;
-  }
 }
 
 // "my ghost partial sums are complete" -> every owner of my ghosts (one block)
-__global__ void __launch_bounds__(kThreads) halo_signal_reverse_kernel(const FusHaloDev h) {
-  __threadfence_system();
+__global__ void __launch_bounds__(32) halo_signal_reverse_kernel(const FusHaloDev h) {
   fus_signal(nullptr, &h.ctr[FUS_CTR_REV_SENT], h.rev_targets, h.n_owner_ranks);
 }
 
-// wait for the REV epoch of every ghosting neighbour, then add their partial sums
+// add the ghosting neighbours' partial sums (their REV epochs have been awaited by halo_wait_kernel)
 template <typename T>
 __global__ void __launch_bounds__(kThreads) halo_get_add_kernel(const FusHaloDev h, const VecArgs<T> a) {
-  const unsigned long long expect = h.ctr[FUS_CTR_REV_WAITED] + 1ULL;
-  fus_wait_flags(h.pad + (long long)FUS_ROW_REV * h.world, h.ghost_ranks, h.n_ghost_ranks, expect, h.ctr);
   const long long stride = (long long)gridDim.x * kThreads;
   for (long long e = (long long)blockIdx.x * kThreads + threadIdx.x; e < h.n; e += stride) {
     const long long li = h.idx[e];
@@ -116,16 +116,11 @@ __global__ void __launch_bounds__(kThreads) halo_get_add_kernel(const FusHaloDev
       }
     }
   }
-  if (fus_last_block(&h.ctr[FUS_CTR_TICKET_GET]) && threadIdx.x == 0) {
-    h.ctr[FUS_CTR_REV_WAITED] = expect;
-    h.ctr[FUS_CTR_TICKET_GET] = 0ULL;
-  }
 }
 
 // neighbour barrier (one block): everything earlier on my stream is visible to the
 // neighbours' later work, and vice versa
-__global__ void __launch_bounds__(kThreads) halo_barrier_kernel(const FusHaloDev h) {
-  __threadfence_system();
+__global__ void __launch_bounds__(32) halo_barrier_kernel(const FusHaloDev h) {
   fus_signal(nullptr, &h.ctr[FUS_CTR_BAR], h.bar_targets, h.n_neigh);
   __syncthreads();
   const unsigned long long expect = h.ctr[FUS_CTR_BAR];
@@ -169,10 +164,15 @@ int wait_forward_entry(fus_halo* h, T* const* zero_vecs, int nzero, void* stream
   FUS_NEED_HANDLE(h, "halo_wait_forward");
   VecArgs<T> z;
   if (int rc = vec_args(z, zero_vecs, nzero, 0, "halo_wait_forward: 0 <= nzero <= 4 non-null vectors")) return rc;
-  if (h->d.n_owner_ranks == 0 && (nzero == 0 || h->d.num_ghosts == 0)) return 0;
-  const unsigned grid = nzero > 0 ? grid_for(h->d.num_ghosts, 2) : 1u;
-  halo_wait_forward_kernel<T><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(h->d, z);
-  FUS_LAUNCH_CHECK("halo_wait_forward_kernel");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (h->d.n_owner_ranks > 0) {
+    halo_wait_kernel<<<1, 32, 0, st>>>(h->d, FUS_ROW_FWD, FUS_CTR_FWD_WAITED, h->d.owner_ranks, h->d.n_owner_ranks);
+    FUS_LAUNCH_CHECK("halo_wait_kernel");
+  }
+  if (nzero > 0 && h->d.num_ghosts > 0) {
+    halo_zero_ghosts_kernel<T><<<grid_for(h->d.num_ghosts, 2), kThreads, 0, st>>>(h->d, z);
+    FUS_LAUNCH_CHECK("halo_zero_ghosts_kernel");
+  }
   return 0;
 }
 
@@ -182,7 +182,10 @@ int get_add_entry(fus_halo* h, T* const* vecs, int nvec, void* stream) {
   VecArgs<T> a;
   if (int rc = vec_args(a, vecs, nvec, 1, "halo_get_add: 1 <= nvec <= 4 non-null vectors")) return rc;
   if (h->d.n_ghost_ranks == 0) return 0;
-  halo_get_add_kernel<T><<<grid_for(h->d.n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(h->d, a);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  halo_wait_kernel<<<1, 32, 0, st>>>(h->d, FUS_ROW_REV, FUS_CTR_REV_WAITED, h->d.ghost_ranks, h->d.n_ghost_ranks);
+  FUS_LAUNCH_CHECK("halo_wait_kernel");
+  halo_get_add_kernel<T><<<grid_for(h->d.n), kThreads, 0, st>>>(h->d, a);
   FUS_LAUNCH_CHECK("halo_get_add_kernel");
   return 0;
 }
@@ -190,7 +193,7 @@ int get_add_entry(fus_halo* h, T* const* vecs, int nvec, void* stream) {
 int signal_reverse_entry(fus_halo* h, void* stream) {
   FUS_NEED_HANDLE(h, "halo_signal_reverse");
   if (h->d.n_owner_ranks == 0) return 0;
-  halo_signal_reverse_kernel<<<1, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(h->d);
+  halo_signal_reverse_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(h->d);
   FUS_LAUNCH_CHECK("halo_signal_reverse_kernel");
   return 0;
 }
@@ -198,7 +201,7 @@ int signal_reverse_entry(fus_halo* h, void* stream) {
 int barrier_entry(fus_halo* h, void* stream) {
   FUS_NEED_HANDLE(h, "halo_barrier");
   if (h->d.n_neigh == 0) return 0;
-  halo_barrier_kernel<<<1, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(h->d);
+  halo_barrier_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(h->d);
   FUS_LAUNCH_CHECK("halo_barrier_kernel");
   return 0;
 }
@@ -254,24 +257,30 @@ int fus_halo_create(const fus_halo_desc_t* desc, fus_halo_t** out) {
       return fus_set_error(FUS_ERR_BAD_ARGUMENT, "halo_create: entry out of range");
   }
 
-  // entries grouped by unique owned dof
+  // Entries grouped by owned dof.  The dofs fus_rk_close_* leaves to fus_rk_close_shared_* are the
+  // shared ones AND the other members of their aligned group of 4 (one float4 / two double2 packs
+  // of the vectorised close kernel), so that kernel can skip whole packs and needs no scalar
+  // path; the extra members have no ghost copies (an empty CSR row: closed, nothing put).
   std::vector<int64_t> order(n);
   std::iota(order.begin(), order.end(), (int64_t)0);
   std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return desc->idx[a] < desc->idx[b]; });
-  std::vector<long long> uniq, uoff, upos(n), seg_delta(ng), idx(n), rpos(n);
+  std::vector<long long> uniq, uoff, upos(n), seg_delta(ng), idx(n), rpos(n), sorted_idx(n);
   std::vector<int> useg(n);
   for (int64_t k = 0; k < n; ++k) {
-    const int64_t e = order[k];
-    if (k == 0 || desc->idx[e] != desc->idx[order[k - 1]]) {
-      uniq.push_back(desc->idx[e]);
-      uoff.push_back(k);
-    }
-    useg[k] = desc->entry_seg[e];
-    upos[k] = desc->remote_pos[e];
+    sorted_idx[k] = desc->idx[order[k]];
+    useg[k] = desc->entry_seg[order[k]];
+    upos[k] = desc->remote_pos[order[k]];
   }
+  for (int64_t k = 0; k < n; ++k) {
+    if (k > 0 && (sorted_idx[k] & ~3LL) == (sorted_idx[k - 1] & ~3LL)) continue;  // group already listed
+    for (long long m = sorted_idx[k] & ~3LL; m < (sorted_idx[k] & ~3LL) + 4 && m < desc->size_local; ++m) uniq.push_back(m);
+  }
+  // CSR row of uniq[i]: the entries whose dof is uniq[i] (none for the non-shared group members)
+  for (long long dd : uniq)
+    uoff.push_back(std::lower_bound(sorted_idx.begin(), sorted_idx.end(), dd) - sorted_idx.begin());
   uoff.push_back(n);
   std::vector<unsigned char> mask((desc->size_local + 7) / 8 + 16, 0);
-  for (long long d : uniq) mask[d >> 3] |= (unsigned char)(1u << (d & 7));
+  for (long long dd : uniq) mask[dd >> 3] |= (unsigned char)(1u << (dd & 7));
   for (int64_t e = 0; e < n; ++e) {
     idx[e] = desc->idx[e];
     rpos[e] = desc->remote_pos[e];

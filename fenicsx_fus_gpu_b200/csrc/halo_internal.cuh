@@ -22,6 +22,7 @@ enum FusHaloCtr {
   FUS_CTR_TICKET_WAIT = 9,
   FUS_CTR_TICKET_GET = 10,
   FUS_CTR_TICKET_CLOSE = 11,
+  FUS_CTR_TICKET_BOUNDARY = 12,
   FUS_CTR_COUNT = 16
 };
 
@@ -80,15 +81,19 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 
-// True in exactly one block of the grid: the last one to arrive.  Every thread's earlier
-// (possibly remote) stores are fenced at system scope before its block takes a ticket.
+// True in exactly one block of the grid: the last one to arrive.  A block's earlier (possibly
+// remote) stores are ordered before its ticket by bar.sync + a GPU-scope fence of thread 0; the
+// last block, having observed every ticket, then issues the ONE system-scope fence of the kernel
+// (fus_signal) - fences are cumulative.  A system-scope fence costs microseconds and serialises
+// across the GPU, so one per block (hundreds per kernel) would put ~20 us on the critical path
+// (measured: tools/mgpu_timeline.py, profiles/r02_multigpu_timeline.md).
 __device__ __forceinline__ bool fus_last_block(unsigned long long* ticket) {
   __shared__ int s_last;
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();
     const unsigned long long t = atomicAdd(ticket, 1ULL);
-    __threadfence_system();
+    __threadfence();
     s_last = (t == (unsigned long long)gridDim.x - 1ULL) ? 1 : 0;
   }
   __syncthreads();
@@ -100,15 +105,13 @@ __device__ __forceinline__ void fus_signal(unsigned long long* ticket, unsigned 
                                            unsigned long long* const* targets, int ntargets) {
   __shared__ unsigned long long s_epoch;
   if (threadIdx.x == 0) {
+    __threadfence_system();  // everything this GPU wrote before (all blocks, earlier kernels) -> system scope
     s_epoch = *sent + 1ULL;
     *sent = s_epoch;
     if (ticket != nullptr) *ticket = 0ULL;
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < ntargets; t += blockDim.x) {
-    __threadfence_system();
-    st_release_sys(targets[t], s_epoch);
-  }
+  for (int t = threadIdx.x; t < ntargets; t += blockDim.x) st_release_sys(targets[t], s_epoch);
 }
 
 // Called by every thread of a block: returns once every flag row[src[t]] >= expect.

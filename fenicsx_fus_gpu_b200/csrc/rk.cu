@@ -244,21 +244,21 @@ __global__ void __launch_bounds__(kThreads, 3) rk_close_kernel(const CloseArgs<T
       if (k < a.n) close_body<T, false, WEST>(a, k);
     }
   } else {
-    // W divides 8: the W dofs of a pack share one mask byte
-    for (long long k = i0; k < nv; k += stride) {
-      const long long d0 = k * W;
-      const unsigned bits = ((unsigned)a.skip[d0 >> 3] >> (unsigned)(d0 & 7)) & ((1u << W) - 1u);
-      if (bits == 0u) {
-        close_body<T, VEC, WEST>(a, k);
-      } else {
-#pragma unroll
-        for (int w = 0; w < W; ++w)
-          if (!((bits >> w) & 1u)) close_body<T, false, WEST>(a, d0 + w);
-      }
+    // The mask marks whole aligned groups of 4 dofs (fus_halo_create), so a pack (W = 2 or 4
+    // dofs, W divides 4) is either closed here or left entirely to rk_close_shared_kernel.  The
+    // mask byte of the NEXT iteration is fetched before this iteration's loads are issued, so
+    // the test never sits in front of the vector loads.
+    long long k = i0;
+    unsigned cur = k < nv ? (unsigned)a.skip[(k * W) >> 3] : 0u;
+    for (; k < nv; k += stride) {
+      const long long kn = k + stride;
+      const unsigned nxt = kn < nv ? (unsigned)a.skip[(kn * W) >> 3] : 0u;
+      if (((cur >> (unsigned)((k * W) & 7)) & 1u) == 0u) close_body<T, VEC, WEST>(a, k);
+      cur = nxt;
     }
     if constexpr (VEC) {
-      const long long k = nv * W + i0;
-      if (k < a.n && !(((unsigned)a.skip[k >> 3] >> (unsigned)(k & 7)) & 1u)) close_body<T, false, WEST>(a, k);
+      const long long kt = nv * W + i0;
+      if (kt < a.n && !(((unsigned)a.skip[kt >> 3] >> (unsigned)(kt & 7)) & 1u)) close_body<T, false, WEST>(a, kt);
     }
   }
   if (a.step != nullptr && (a.next_mode == 2 || a.next_mode == 4) && i0 == 0) *a.step += 1;
@@ -292,13 +292,16 @@ __global__ void __launch_bounds__(kThreads) rk_close_shared_kernel(const CloseAr
   }
 }
 
-// b[dof[i]] += g*src[i] + dg*src2[i] + vn[dof[i]]*absb[i]; the dof list is unique
-template <typename T>
+// b[dof[i]] += g*src[i] + dg*src2[i] + vn[dof[i]]*absb[i]; the dof list is unique.
+// SIGNAL (multi-GPU): this is the last kernel of a stage that writes ghost partial sums, so its
+// last block raises the REV epoch on every owner of my ghosts (= fus_halo_signal_reverse, without
+// a launch of its own on the critical path).
+template <typename T, bool SIGNAL>
 __global__ void __launch_bounds__(kThreads)
     boundary_kernel(T* b, const T* __restrict__ vn, const int32_t* __restrict__ dof,
                     const T* __restrict__ src, const T* __restrict__ src2,
                     const T* __restrict__ absb, T g, T dg, const T* __restrict__ gtab,
-                    const long long* __restrict__ step, int gstride, int goff, long long n) {
+                    const long long* __restrict__ step, int gstride, int goff, long long n, const FusHaloDev h) {
   if (gtab != nullptr) {
     const long long s = step != nullptr ? *step : 0;
     g = gtab[s * gstride + goff];
@@ -312,6 +315,10 @@ __global__ void __launch_bounds__(kThreads)
     if (src2 != nullptr) acc += dg * src2[i];
     if (absb != nullptr) acc += vn[d] * absb[i];
     b[d] += acc;
+  }
+  if constexpr (SIGNAL) {
+    if (fus_last_block(&h.ctr[FUS_CTR_TICKET_BOUNDARY]))
+      fus_signal(&h.ctr[FUS_CTR_TICKET_BOUNDARY], &h.ctr[FUS_CTR_REV_SENT], h.rev_targets, h.n_owner_ranks);
   }
 }
 
@@ -401,12 +408,19 @@ int close_shared_entry(fus_halo* halo, int variant, int put_next, T* u, T* v, T*
 template <typename T>
 int boundary_entry(T* b, const T* vn, const int32_t* dof, const T* src, const T* src2,
                    const T* absb, T g, T dg, const T* gtab, const int64_t* step, int gstride,
-                   int goff, int64_t n, void* stream) {
+                   int goff, int64_t n, void* stream, fus_halo* halo = nullptr) {
   if (n < 0) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "boundary_terms: n < 0");
-  if (n == 0) return 0;
-  boundary_kernel<T><<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      b, vn, dof, src, src2, absb, g, dg, gtab, reinterpret_cast<const long long*>(step), gstride,
-      goff, n);
+  const bool signal = halo != nullptr && fus_halo_dev_of(halo)->n_owner_ranks > 0;
+  if (n == 0 && !signal) return 0;
+  cudaStream_t st_ = static_cast<cudaStream_t>(stream);
+  const long long* stp = reinterpret_cast<const long long*>(step);
+  if (signal) {
+    boundary_kernel<T, true><<<grid_for(n), kThreads, 0, st_>>>(b, vn, dof, src, src2, absb, g, dg, gtab, stp,
+                                                                gstride, goff, n, *fus_halo_dev_of(halo));
+  } else {
+    boundary_kernel<T, false><<<grid_for(n), kThreads, 0, st_>>>(b, vn, dof, src, src2, absb, g, dg, gtab, stp,
+                                                                 gstride, goff, n, FusHaloDev{});
+  }
   FUS_LAUNCH_CHECK("boundary_kernel");
   return 0;
 }
@@ -451,6 +465,15 @@ extern "C" {
                                void* s) {                                                        \
     return boundary_entry<T>(b, vn, dof, src, src2, absb, g, dg, gtab, step_dev, gstride, goff,  \
                              n, s);                                                              \
+  }                                                                                              \
+  int fus_boundary_terms_signal_##SFX(fus_halo_t* halo, T* b, const T* vn, const int32_t* dof,   \
+                                      const T* src, const T* src2, const T* absb, T g, T dg,     \
+                                      const T* gtab, const int64_t* step_dev, int gstride,       \
+                                      int goff, int64_t n, void* s) {                            \
+    if (halo == nullptr)                                                                         \
+      return fus_set_error(FUS_ERR_BAD_ARGUMENT, "boundary_terms_signal: null halo handle");     \
+    return boundary_entry<T>(b, vn, dof, src, src2, absb, g, dg, gtab, step_dev, gstride, goff,  \
+                             n, s, halo);                                                        \
   }
 
 FUS_RK_API(f64, double)

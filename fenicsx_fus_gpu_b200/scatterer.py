@@ -373,6 +373,9 @@ def scatter_reverse(comm, owners_data, ghosts_data, N, float_type):
 # --------------------------------------------------------------------------- #
 
 
+SLOT = 1 << 21
+
+
 class SymmFabric:
     """Peer-addressable device memory for one process per GPU: a symmetric
     arena (``torch.distributed._symmetric_memory``: CUDA VMM allocations mapped
@@ -392,7 +395,7 @@ class SymmFabric:
         self.size = dist.get_world_size(self.group)
         t = torch.tensor([int(arena_bytes)], dtype=torch.int64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)  # same size everywhere
-        self.arena_bytes = (int(t.item()) + 255) // 256 * 256
+        self.arena_bytes = (int(t.item()) + SLOT - 1) // SLOT * SLOT
         self.arena = symm.empty(self.arena_bytes, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
         self.arena.zero_()
         self.hdl = symm.rendezvous(self.arena, self.group)
@@ -408,7 +411,10 @@ class SymmFabric:
         import torch
 
         item = torch.empty(0, dtype=tdtype).element_size()
-        slot = (int(slot_numel if slot_numel is not None else numel) * item + 255) // 256 * 256
+        # Slots are multiples of 2 MiB: vectors that start at the same offset of a 2 MiB page stream
+        # ~2 % faster through the 12-vector close kernel than vectors at arbitrary offsets (measured,
+        # tools/close_bench.py: plain device memory carved at 256-byte granularity shows the same loss)
+        slot = (int(slot_numel if slot_numel is not None else numel) * item + SLOT - 1) // SLOT * SLOT
         if self._used + slot > self.arena_bytes:
             raise RuntimeError("SymmFabric: arena exhausted")
         out = self.arena[self._used:self._used + numel * item].view(tdtype)
@@ -456,7 +462,7 @@ class _LocalFabric:
         import torch
 
         self.cluster, self.rank, self.size = cluster, rank, cluster.size
-        self.arena_bytes = (self.max_over_ranks(arena_bytes) + 255) // 256 * 256
+        self.arena_bytes = (self.max_over_ranks(arena_bytes) + SLOT - 1) // SLOT * SLOT
         self.arena = torch.zeros(self.arena_bytes, dtype=torch.uint8, device="cuda")
         with cluster._lock:
             cluster._mail[("arena", rank)] = self.arena
@@ -590,7 +596,7 @@ class P2PHaloExchange:
     @staticmethod
     def arena_bytes(ndofs_local: int, float_type, nvec: int = 12) -> int:
         """Arena size for ``nvec`` exchanged vectors of ``ndofs_local`` entries (+ the signal pad)."""
-        return nvec * ((int(ndofs_local) * np.dtype(float_type).itemsize + 255) // 256 * 256 + 256) + 4096
+        return (nvec * ((int(ndofs_local) * np.dtype(float_type).itemsize + SLOT - 1) // SLOT) + 1) * SLOT
 
     def alloc(self):
         """A zeroed ``(N + nghost,)`` vector in peer-addressable memory."""

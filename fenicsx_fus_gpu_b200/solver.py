@@ -336,16 +336,20 @@ class _RK4:
     def _ptr(self, t):
         return None if t is None else t.data_ptr()
 
-    def _boundary(self, stage, g, dg, use_table, vn):
+    def _boundary(self, stage, g, dg, use_table, vn, signal=False):
+        """b += g*src + dg*src2 + vn*absb on the boundary dofs.  ``signal`` (peer-memory halo): the
+        launch also raises the "ghost sums complete" epoch (and happens even without boundary dofs)."""
         nb = int(self._bdofs.numel())
-        if not nb:
+        if not nb and not signal:
             return
-        check(fn("fus_boundary_terms", self.dtype)(
-            self.b.data_ptr(), vn.data_ptr(), self._bdofs.data_ptr(), self._ptr(self._src),
-            self._ptr(self._src2), self._ptr(self._absb), float(g), float(dg),
-            self.gtab.data_ptr() if use_table else None,
-            self.step_dev.data_ptr() if use_table else None, 8, 2 * stage, nb, current_stream()),
-            "fus_boundary_terms")
+        args = (self.b.data_ptr(), vn.data_ptr(), self._bdofs.data_ptr() if nb else None, self._ptr(self._src),
+                self._ptr(self._src2), self._ptr(self._absb), float(g), float(dg),
+                self.gtab.data_ptr() if use_table else None,
+                self.step_dev.data_ptr() if use_table else None, 8, 2 * stage, nb, current_stream())
+        if signal:
+            check(fn("fus_boundary_terms_signal", self.dtype)(self.halo.handle, *args), "fus_boundary_terms_signal")
+        else:
+            check(fn("fus_boundary_terms", self.dtype)(*args), "fus_boundary_terms")
 
     def _open_first(self):
         """b = 0 before the first stage (cuda/demo_linear_box.py:541); the stage-0 input is the
@@ -404,7 +408,8 @@ class _RK4:
         h = self.halo
         accum = (self.b, self.m) if self._m_accum else (self.b,)
         interior = "interior" if "interior" in self._phases else None
-        h.put(*base)  # stage-0 input -> the neighbours' ghost slots
+        # the stage-0 input (the base state) is already on its way to the neighbours' ghost
+        # slots: put there by begin_steps() or by the last stage of the previous step
         for i in range(4):
             g = dg = 0.0
             if not use_table and self.source is not None:
@@ -417,14 +422,26 @@ class _RK4:
                 self._assemble(i, g, dg, use_table, x, vn, "interior")
             h.join()
             self._assemble(i, g, dg, use_table, x, vn, "interface" if interior else "all")
-            self._boundary(i, g, dg, use_table, vn)
-            h.signal_reverse()
+            self._boundary(i, g, dg, use_table, vn, signal=True)  # + "my ghost sums are complete"
             h.fork()
             with h.side():
                 h.get_add(*accum)
-                self._close_shared(i, dt, base, acc)  # + put of the next stage input (not after the last stage)
+                self._close_shared(i, dt, base, acc)  # + put of the next stage's / next step's input
             self._close(i, dt, use_table, base, acc, skip=h.shared_mask)
             h.join()
+
+    def begin_steps(self):
+        """Peer-memory halo: send the current state to the neighbours' ghost slots before a run
+        of steps (every step then ends by putting the next one's input).  Collective; a no-op
+        otherwise."""
+        if self.p2p:
+            self.halo.barrier()  # the neighbours are done reading the ghost values about to be replaced
+            self.halo.put(*self._uv[self._parity])
+
+    def end_steps(self):
+        """Consume the put the last step of a run left pending (keeps puts and waits paired)."""
+        if self.p2p:
+            self.halo.wait_forward()
 
     def _close_args(self, stage, dt, base, acc):
         """(u, v, u0, v0 pointers, bdt, adt_next, next_mode) of the close kernel for ``stage``:
@@ -471,12 +488,16 @@ class _RK4:
         if self.use_graph:
             if self._graph_dt != dt or self._graph_tab != self.gtab.data_ptr():
                 self._capture(dt)
+            self.begin_steps()
             for _ in range(nsteps):
                 self._replay_step(dt)
+            self.end_steps()
         else:
+            self.begin_steps()
             for k in range(nsteps):
                 self._enqueue_step(dt, 0.0, True)
                 self._parity ^= 1
+            self.end_steps()
         for _ in range(nsteps):
             self.t += dt
         self.nstep += nsteps
@@ -497,8 +518,10 @@ class _RK4:
         self._set_tables()
         if not self._opened:
             self._open_first()
+        self.begin_steps()
         self._enqueue_step(dt, self.t, False)
         self._parity ^= 1
+        self.end_steps()
         self.t += dt
         self.nstep += 1
         return self.t
@@ -522,8 +545,10 @@ class _RK4:
         # warm up outside capture (lazy NCCL communicators, module loading)
         saved = [t.clone() for t in self._state()]
         step0 = self.step_dev.clone()
-        for parity in (self._parity, 1 - self._parity):  # both buffer roles (halo peer tables are built lazily)
+        self.begin_steps()
+        for parity in (self._parity, 1 - self._parity):  # both buffer roles, each step feeding the next
             self._enqueue_step(dt, 0.0, True, parity)
+        self.end_steps()
         torch.cuda.synchronize()
         for t, s in zip(self._state(), saved):
             t.copy_(s)
@@ -630,7 +655,7 @@ class LinearSpectral3D(_RK4):
     def _close_shared(self, stage, dt, base, acc):
         u, v, u0, v0, bdt, adt, mode = self._close_args(stage, dt, base, acc)
         check(fn("fus_rk_close_shared", self.dtype)(
-            self.halo.handle, 0, int(stage < 3), u, v, u0, v0, self.ku.data_ptr(), self.un.data_ptr(),
+            self.halo.handle, 0, 1, u, v, u0, v0, self.ku.data_ptr(), self.un.data_ptr(),
             self.b.data_ptr(), self.m.data_ptr(), None, None, None, bdt, adt, mode, current_stream()),
             "fus_rk_close_shared")
 
@@ -765,7 +790,7 @@ class WesterveltSpectral3D(_RK4):
         u, v, u0, v0, bdt, adt, mode = self._close_args(stage, dt, base, acc)
         pw = not self._m_accum
         check(fn("fus_rk_close_shared", self.dtype)(
-            self.halo.handle, 2 if pw else 1, int(stage < 3), u, v, u0, v0, self.ku.data_ptr(), self.un.data_ptr(),
+            self.halo.handle, 2 if pw else 1, 1, u, v, u0, v0, self.ku.data_ptr(), self.un.data_ptr(),
             self.b.data_ptr(), None if pw else self.m.data_ptr(), self.m0.data_ptr(),
             self.m2.data_ptr() if pw else None, self.m5.data_ptr() if pw else None, bdt, adt, mode,
             current_stream()), "fus_rk_close_shared")

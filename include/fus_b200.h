@@ -270,8 +270,10 @@ int64_t fus_halo_pad_bytes(int world);
  * `desc` are copied.  Collective only in the sense that every rank must create its own. */
 int fus_halo_create(const fus_halo_desc_t* desc, fus_halo_t** out);
 int fus_halo_destroy(fus_halo_t* h);
-/* unique owned dofs that are ghosts somewhere, and the bitmask over [0, size_local)
- * (bit d%8 of byte d/8) that fus_rk_close_* takes as skip_mask (DEVICE pointer). */
+/* The owned dofs fus_rk_close_shared_* closes - those that are ghosts somewhere plus the other
+ * members of their aligned groups of 4 (so the vectorised close kernel skips whole packs) - and
+ * the bitmask over [0, size_local) marking them (bit d%8 of byte d/8), which fus_rk_close_* takes
+ * as skip_mask (DEVICE pointer). */
 int64_t fus_halo_num_shared(const fus_halo_t* h);
 const uint8_t* fus_halo_shared_mask(const fus_halo_t* h);
 /* 0, or FUS_ERR_HALO_TIMEOUT when a wait gave up (a neighbour never signalled). Synchronous. */
@@ -387,6 +389,18 @@ int fus_boundary_terms_f32(float* b, const float* vn, const int32_t* dof, const 
                            const float* src2, const float* absb, float g, float dg,
                            const float* gtab, const int64_t* step_dev, int gstride, int goff,
                            int64_t n, void* stream);
+
+/* The same, followed by fus_halo_signal_reverse(halo) from the kernel's last block: in a multi-GPU
+ * stage the boundary terms are the last writes into the ghost partial sums, so the "my sums are
+ * complete" epoch rides on this launch instead of needing one of its own (n may be 0). */
+int fus_boundary_terms_signal_f64(fus_halo_t* halo, double* b, const double* vn, const int32_t* dof,
+                                  const double* src, const double* src2, const double* absb, double g,
+                                  double dg, const double* gtab, const int64_t* step_dev, int gstride,
+                                  int goff, int64_t n, void* stream);
+int fus_boundary_terms_signal_f32(fus_halo_t* halo, float* b, const float* vn, const int32_t* dof,
+                                  const float* src, const float* src2, const float* absb, float g,
+                                  float dg, const float* gtab, const int64_t* step_dev, int gstride,
+                                  int goff, int64_t n, void* stream);
 
 /* Westervelt stage helpers (cuda/demo_nonlinear_bowl.py:603-650):
  *   w = vn*vn                                                   (:603)

@@ -24,6 +24,9 @@ def main():
     ap.add_argument("--n", type=int, default=80)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--fake-p2p", action="store_true",
+                    help="1 GPU: a one-rank peer-memory halo (no neighbours) - vectors in the symmetric arena and the "
+                         "skip mask passed to the close kernel, nothing exchanged: their cost in situ")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -56,7 +59,22 @@ def main():
         return float(t.item())
 
     out = {"n_gpus": world, "n": a.n}
-    solver, info = bench.build_problem(rank, world, a.n, np.float64, "p2p", "linear_box", 4, "stream")
+    if a.fake_p2p:
+        from fenicsx_fus_gpu_b200 import problem
+        from fenicsx_fus_gpu_b200.scatterer import P2PHaloExchange, SymmFabric
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29578")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+        h = 0.12 / 80
+        su = problem.box_setup(4, a.n, h * a.n, np.float64)
+        fab = SymmFabric(P2PHaloExchange.arena_bytes(su.ndofs, np.float64))
+        e = [[], np.zeros(0, np.int32), np.zeros(0, np.int32)]
+        su.halo = P2PHaloExchange(fab, e, e, su.ndofs, 0, np.float64)
+        solver = problem.linear_solver(su, source_facets=[2], absorbing_facets=[3], p0=60000.0)
+        info = {"dt": problem.cfl_time_step(4, h, 1500.0, 0.5e6, 0.65)}
+    else:
+        solver, info = bench.build_problem(rank, world, a.n, np.float64, "p2p", "linear_box", 4, "stream")
     dt = info["dt"]
     out["graph_ms_per_step"] = timed_graph(solver, dt, a.steps)
     out["graph_ms_per_step_again"] = timed_graph(solver, dt, a.steps)
@@ -88,10 +106,10 @@ def main():
 
     wrap(solver, "_assemble", lambda *x, **k: "stiffness:" + (x[6] if len(x) > 6 else "all"))
     wrap(solver, "_boundary", "boundary")
-    wrap(solver, "_close", "close" + ("(masked)" if world > 1 else ""))
-    if world > 1:
+    wrap(solver, "_close", lambda *x, **k: f"close{'(masked)' if solver.p2p else ''}[stage {x[0]}]")
+    if solver.p2p:
         wrap(solver, "_close_shared", "close_shared+put")
-        for nm in ("put", "wait_forward", "signal_reverse", "get_add"):
+        for nm in ("put", "wait_forward", "signal_reverse", "get_add", "barrier"):
             wrap(solver.halo, nm, "halo." + nm)
     solver.use_graph = False
     solver.init()
@@ -125,8 +143,9 @@ def main():
                       f"  = {v['ms_per_step']:.3f} ms/step")
         if a.out:
             json.dump(allo, open(a.out, "w"), indent=1)
-    if world > 1:
-        dist.barrier()
+    if world > 1 or a.fake_p2p:
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
         os._exit(0)
 
