@@ -302,6 +302,9 @@ def main():
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU halo: fused put/get kernels over NVLink peer memory, or NCCL send/recv")
     ap.add_argument("--no-split", action="store_true", help="p2p halo without the interior/interface cell split (A/B)")
+    ap.add_argument("--split-mode", default="none", choices=["none", "two", "fused"],
+                    help="p2p halo: wait, then all cells in one launch (default); interface cells in a second launch; "
+                         "or in the same launch behind an in-kernel wait (A/B, see solver.py)")
     ap.add_argument("--no-graph", action="store_true", help="launch the steps eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-kind", default=None, choices=["numba", "cpp", "port"], help="CPU arm implementation")
     ap.add_argument("--sustain-steps", type=int, default=250, help="steps of the extra >= 1 s sustained measurement")
@@ -430,14 +433,16 @@ def main():
     config["geometry"] = ("G streamed (reference data flow)" if a.geometry == "stream" else
                           f"auto: {solver.nrect} rectilinear + {solver.naff - solver.nrect} affine of {solver.ncells} "
                           "cells per GPU keep 6 geometric factors instead of 6 n^3")
-    halo_txt = {"p2p": "fused put/get kernels over NVLink peer memory, epoch-flag signalling, exchange overlapped "
-                       "with interior-cell stiffness and the non-shared part of the close",
+    halo_txt = {"p2p": "NVLink peer memory + per-neighbour epoch flags, no barrier: one kernel gathers the ghost sums, "
+                       "closes the shared dofs and puts the next stage input into the neighbours' ghost slots while "
+                       f"the close of the non-shared dofs runs (split_mode={a.split_mode})",
                 "nccl": "NCCL send/recv", "none": "none (1 GPU)"}[info["halo"]]
     config["parallelism"] = f"block partition x{world}, halo: {halo_txt}"
     if world > 1 and info["halo"] == "p2p":
         config["interface_cells_per_gpu"] = int(solver.ninterface)
         config["shared_dofs_per_gpu"] = int(solver.halo.nshared)
     solver.use_graph = not a.no_graph
+    solver.split_mode = a.split_mode
     log(f"problem built: {info['ndofs_local']} local dofs, {info['ncells_local']} cells")
     dt = info["dt"]
 
@@ -626,7 +631,7 @@ def main():
                                                                "of this kernel (profiles/stiffness_traffic.json)",
                 "peak_kind": peak_kind, "algorithmic_bytes_per_launch": bytes_stiff, "launch_ms": t_in_step * 1e3,
                 "launches_timed": n_probed, "timing": "CUDA events around every launch of the kernel inside the RK steps"
-                                                      + (" (interior + interface launches summed per stage)" if n_probed > 4 * nprobe else ""),
+,
                 "standalone": {"launch_ms": t_stiff * 1e3, "launch_ms_min": t_stiff_min * 1e3, "launches_timed": reps,
                                "achieved": bytes_stiff / t_stiff / 1e9, "frac": bytes_stiff / t_stiff / 1e9 / peak,
                                "timing": "back-to-back launches between one event pair"}}

@@ -61,10 +61,10 @@ def _sigs():
         "fus_halo_reverse": [P, P, I, P],
         "fus_rk_open": [P, P, P, P, P, P, P, P, T, I, L, P],
         "fus_rk_close": [P, P, P, P, P, P, P, P, P, T, T, I, L, P, P, P],
-        "fus_rk_close_shared": [P, I, I, P, P, P, P, P, P, P, P, P, P, P, T, T, I, P],
+        "fus_rk_close_shared": [P, I, I, I, P, P, P, P, P, P, P, P, P, P, P, T, T, I, P],
         "fus_rk_close_westervelt": [P, P, P, P, P, P, P, P, P, P, T, T, I, L, P, P, P],
         "fus_boundary_terms": [P, P, P, P, P, P, T, T, P, P, I, I, L, P],
-        "fus_boundary_terms_signal": [P, P, P, P, P, P, P, T, T, P, P, I, I, L, P],
+        "fus_boundary_terms_signal": [P, P, P, P, P, P, P, T, T, P, P, I, I, L, I, P],
         "fus_westervelt_mass": [P, P, P, P, P, P, P, P, L, I, P],
         "fus_geometry": [P, P, P, P, P, P, L, I, P],
         "fus_facet_geometry": [P, P, P, P, P, P, L, I, P],
@@ -77,7 +77,8 @@ def _sigs():
 #: every symbol include/fus_b200.h declares (checked by tests/test_abi.py)
 UNTYPED = ["fus_abi_version", "fus_last_error", "fus_launch_count", "fus_reset_launch_count",
            "fus_halo_pad_bytes", "fus_halo_create", "fus_halo_destroy", "fus_halo_num_shared",
-           "fus_halo_shared_mask", "fus_halo_status", "fus_halo_signal_reverse", "fus_halo_barrier"]
+           "fus_halo_shared_mask", "fus_halo_status", "fus_halo_signal_reverse", "fus_halo_barrier",
+           "fus_halo_wait_reverse", "fus_stiffness_arm_halo_wait"]
 
 
 class HaloDesc(C.Structure):
@@ -121,6 +122,8 @@ def lib():
     lb.fus_halo_status.restype, lb.fus_halo_status.argtypes = I, [P]
     lb.fus_halo_signal_reverse.restype, lb.fus_halo_signal_reverse.argtypes = I, [P, P]
     lb.fus_halo_barrier.restype, lb.fus_halo_barrier.argtypes = I, [P, P]
+    lb.fus_halo_wait_reverse.restype, lb.fus_halo_wait_reverse.argtypes = I, [P, P]
+    lb.fus_stiffness_arm_halo_wait.restype, lb.fus_stiffness_arm_halo_wait.argtypes = I, [P, L]
     for base, args in _sigs().items():
         for sfx, ft in (("f64", C.c_double), ("f32", C.c_float)):
             fn = getattr(lb, f"{base}_{sfx}", None)

@@ -2,10 +2,12 @@
 #include <atomic>
 #include <cstdio>
 
-#include "fus_common.cuh"
+#include "halo_internal.cuh"
 
 namespace {
 thread_local char g_err[512] = "";
+thread_local const FusHaloDev* g_armed_halo = nullptr;
+thread_local long long g_armed_from = 0;
 std::atomic<long long> g_launches{0};
 }  // namespace
 
@@ -33,7 +35,20 @@ int fus_num_sms() {
   return sms[dev];
 }
 
+bool fus_take_armed_wait(const FusHaloDev** h, long long* first_interface_cell) {
+  if (g_armed_halo == nullptr) return false;
+  *h = g_armed_halo;
+  *first_interface_cell = g_armed_from;
+  g_armed_halo = nullptr;
+  return true;
+}
+
 extern "C" {
+int fus_stiffness_arm_halo_wait(const fus_halo_t* halo, int64_t first_interface_cell) {
+  g_armed_halo = halo == nullptr ? nullptr : fus_halo_dev_of(halo);
+  g_armed_from = first_interface_cell;
+  return 0;
+}
 int fus_abi_version(void) { return FUS_ABI_VERSION; }
 const char* fus_last_error(void) { return g_err; }
 int64_t fus_launch_count(void) { return g_launches.load(); }

@@ -25,6 +25,10 @@ void fus_count_launch(int n = 1);
 
 int fus_num_sms();
 
+// halo wait armed for the next stiffness launch of this host thread (api.cu)
+struct FusHaloDev;
+bool fus_take_armed_wait(const FusHaloDev** h, long long* first_interface_cell);
+
 // stiffness_affine.cu keeps its own copy of the derivative tables (fus_set_dphi_* fills both)
 int fus_affine_set_dphi_f64(int P, const double* dphi, void* stream);
 int fus_affine_set_dphi_f32(int P, const float* dphi, void* stream);

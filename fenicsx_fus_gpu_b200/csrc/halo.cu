@@ -176,6 +176,8 @@ int wait_forward_entry(fus_halo* h, T* const* zero_vecs, int nzero, void* stream
   return 0;
 }
 
+int wait_reverse_entry(fus_halo* h, void* stream);
+
 template <typename T>
 int get_add_entry(fus_halo* h, T* const* vecs, int nvec, void* stream) {
   FUS_NEED_HANDLE(h, "halo_get_add");
@@ -183,10 +185,18 @@ int get_add_entry(fus_halo* h, T* const* vecs, int nvec, void* stream) {
   if (int rc = vec_args(a, vecs, nvec, 1, "halo_get_add: 1 <= nvec <= 4 non-null vectors")) return rc;
   if (h->d.n_ghost_ranks == 0) return 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  halo_wait_kernel<<<1, 32, 0, st>>>(h->d, FUS_ROW_REV, FUS_CTR_REV_WAITED, h->d.ghost_ranks, h->d.n_ghost_ranks);
-  FUS_LAUNCH_CHECK("halo_wait_kernel");
+  if (int rc = wait_reverse_entry(h, stream)) return rc;
   halo_get_add_kernel<T><<<grid_for(h->d.n), kThreads, 0, st>>>(h->d, a);
   FUS_LAUNCH_CHECK("halo_get_add_kernel");
+  return 0;
+}
+
+int wait_reverse_entry(fus_halo* h, void* stream) {
+  FUS_NEED_HANDLE(h, "halo_wait_reverse");
+  if (h->d.n_ghost_ranks == 0) return 0;
+  halo_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(h->d, FUS_ROW_REV, FUS_CTR_REV_WAITED,
+                                                                     h->d.ghost_ranks, h->d.n_ghost_ranks);
+  FUS_LAUNCH_CHECK("halo_wait_kernel");
   return 0;
 }
 
@@ -374,6 +384,7 @@ int fus_halo_status(fus_halo_t* h) {
 }
 
 int fus_halo_signal_reverse(fus_halo_t* h, void* stream) { return signal_reverse_entry(h, stream); }
+int fus_halo_wait_reverse(fus_halo_t* h, void* stream) { return wait_reverse_entry(h, stream); }
 int fus_halo_barrier(fus_halo_t* h, void* stream) { return barrier_entry(h, stream); }
 
 #define FUS_HALO_API(SFX, T)                                                                      \

@@ -269,16 +269,38 @@ __global__ void __launch_bounds__(kThreads, 3) rk_close_kernel(const CloseArgs<T
 // NEXT stage: the fresh stage input (un, vn = ku; or the new state u, v after the last
 // stage) goes straight from registers into the neighbours' ghost slots, then the FWD epoch.
 template <typename T, int WEST>
-__global__ void __launch_bounds__(kThreads) rk_close_shared_kernel(const CloseArgs<T> a, const FusHaloDev h, int put) {
+__global__ void __launch_bounds__(kThreads) rk_close_shared_kernel(const CloseArgs<T> a, const FusHaloDev h, int put,
+                                                                   int gather) {
   const long long stride = (long long)gridDim.x * kThreads;
   T* const xa = a.next_mode == 4 ? a.u : a.un;
   T* const xb = a.next_mode == 4 ? a.v : a.ku;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < h.nu; i += stride) {
     const long long k = h.uniq[i];
+    const long long j0 = h.uoff[i], j1 = h.uoff[i + 1];
+    if (gather && j1 > j0) {
+      // reverse halo, fused: add the neighbours' ghost partial sums of this dof (loaded straight
+      // from their vectors) and clear them there for the next stage; the local assembly of b[k]
+      // finished before this kernel, and nobody else touches dof k now
+      T sb = T(0), sm = T(0);
+      for (long long j = j0; j < j1; ++j) {
+        const long long dl = h.seg_delta[h.useg[j]];
+        const long long rp = h.upos[j];
+        T* rb = reinterpret_cast<T*>(reinterpret_cast<char*>(a.b) + dl) + rp;
+        sb += *reinterpret_cast<volatile const T*>(rb);
+        *rb = T(0);
+        if constexpr (WEST == 1) {
+          T* rm = reinterpret_cast<T*>(reinterpret_cast<char*>(a.m) + dl) + rp;
+          sm += *reinterpret_cast<volatile const T*>(rm);
+          *rm = T(0);
+        }
+      }
+      a.b[k] += sb;
+      if constexpr (WEST == 1) a.m[k] += sm;
+    }
     close_body<T, false, WEST>(a, k);
     if (put) {
       const T va = xa[k], vb = xb[k];
-      for (long long j = h.uoff[i]; j < h.uoff[i + 1]; ++j) {
+      for (long long j = j0; j < j1; ++j) {
         const long long dl = h.seg_delta[h.useg[j]];
         const long long rp = h.upos[j];
         reinterpret_cast<T*>(reinterpret_cast<char*>(xa) + dl)[rp] = va;
@@ -301,7 +323,8 @@ __global__ void __launch_bounds__(kThreads)
     boundary_kernel(T* b, const T* __restrict__ vn, const int32_t* __restrict__ dof,
                     const T* __restrict__ src, const T* __restrict__ src2,
                     const T* __restrict__ absb, T g, T dg, const T* __restrict__ gtab,
-                    const long long* __restrict__ step, int gstride, int goff, long long n, const FusHaloDev h) {
+                    const long long* __restrict__ step, int gstride, int goff, long long n, const FusHaloDev h,
+                    int consume_fwd) {
   if (gtab != nullptr) {
     const long long s = step != nullptr ? *step : 0;
     g = gtab[s * gstride + goff];
@@ -317,8 +340,12 @@ __global__ void __launch_bounds__(kThreads)
     b[d] += acc;
   }
   if constexpr (SIGNAL) {
-    if (fus_last_block(&h.ctr[FUS_CTR_TICKET_BOUNDARY]))
+    if (fus_last_block(&h.ctr[FUS_CTR_TICKET_BOUNDARY])) {
+      // the stiffness launches of this stage have consumed one FWD epoch (their in-kernel wait
+      // reads the counter, this kernel - the next one on the stream - advances it)
+      if (threadIdx.x == 0 && consume_fwd) h.ctr[FUS_CTR_FWD_WAITED] += 1ULL;
       fus_signal(&h.ctr[FUS_CTR_TICKET_BOUNDARY], &h.ctr[FUS_CTR_REV_SENT], h.rev_targets, h.n_owner_ranks);
+    }
   }
 }
 
@@ -376,7 +403,7 @@ int close_entry(T* u, T* v, T* u0, T* v0, T* ku, T* kv, T* un, T* b, T* m, const
 
 // variant 0: linear, 1: Westervelt "cells" form, 2: Westervelt pointwise form
 template <typename T>
-int close_shared_entry(fus_halo* halo, int variant, int put_next, T* u, T* v, T* u0, T* v0, T* ku, T* un, T* b,
+int close_shared_entry(fus_halo* halo, int variant, int put_next, int gather, T* u, T* v, T* u0, T* v0, T* ku, T* un, T* b,
                        T* m, const T* m0, const T* m2, const T* m5, T bdt, T adt_next, int next_mode,
                        void* stream) {
   if (halo == nullptr) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close_shared: null halo handle");
@@ -393,13 +420,13 @@ int close_shared_entry(fus_halo* halo, int variant, int put_next, T* u, T* v, T*
   const long long cap = (long long)fus_num_sms() * 4;
   if (blocks > cap) blocks = cap;
   cudaStream_t st_ = static_cast<cudaStream_t>(stream);
-  const int put = put_next ? 1 : 0;
+  const int put = put_next ? 1 : 0, gat = gather ? 1 : 0;
   if (variant == 0) {
-    rk_close_shared_kernel<T, 0><<<(unsigned)blocks, kThreads, 0, st_>>>(a, h, put);
+    rk_close_shared_kernel<T, 0><<<(unsigned)blocks, kThreads, 0, st_>>>(a, h, put, gat);
   } else if (variant == 1) {
-    rk_close_shared_kernel<T, 1><<<(unsigned)blocks, kThreads, 0, st_>>>(a, h, put);
+    rk_close_shared_kernel<T, 1><<<(unsigned)blocks, kThreads, 0, st_>>>(a, h, put, gat);
   } else {
-    rk_close_shared_kernel<T, 2><<<(unsigned)blocks, kThreads, 0, st_>>>(a, h, put);
+    rk_close_shared_kernel<T, 2><<<(unsigned)blocks, kThreads, 0, st_>>>(a, h, put, gat);
   }
   FUS_LAUNCH_CHECK("rk_close_shared_kernel");
   return 0;
@@ -408,7 +435,7 @@ int close_shared_entry(fus_halo* halo, int variant, int put_next, T* u, T* v, T*
 template <typename T>
 int boundary_entry(T* b, const T* vn, const int32_t* dof, const T* src, const T* src2,
                    const T* absb, T g, T dg, const T* gtab, const int64_t* step, int gstride,
-                   int goff, int64_t n, void* stream, fus_halo* halo = nullptr) {
+                   int goff, int64_t n, void* stream, fus_halo* halo = nullptr, int consume_fwd = 0) {
   if (n < 0) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "boundary_terms: n < 0");
   const bool signal = halo != nullptr && fus_halo_dev_of(halo)->n_owner_ranks > 0;
   if (n == 0 && !signal) return 0;
@@ -416,10 +443,10 @@ int boundary_entry(T* b, const T* vn, const int32_t* dof, const T* src, const T*
   const long long* stp = reinterpret_cast<const long long*>(step);
   if (signal) {
     boundary_kernel<T, true><<<grid_for(n), kThreads, 0, st_>>>(b, vn, dof, src, src2, absb, g, dg, gtab, stp,
-                                                                gstride, goff, n, *fus_halo_dev_of(halo));
+                                                                gstride, goff, n, *fus_halo_dev_of(halo), consume_fwd);
   } else {
     boundary_kernel<T, false><<<grid_for(n), kThreads, 0, st_>>>(b, vn, dof, src, src2, absb, g, dg, gtab, stp,
-                                                                 gstride, goff, n, FusHaloDev{});
+                                                                 gstride, goff, n, FusHaloDev{}, 0);
   }
   FUS_LAUNCH_CHECK("boundary_kernel");
   return 0;
@@ -440,11 +467,12 @@ extern "C" {
     return close_entry<T, 0>(u, v, u0, v0, ku, kv, un, b, const_cast<T*>(m), nullptr, bdt,       \
                              adt_next, next_mode, n, step_dev, skip_mask, s);                    \
   }                                                                                              \
-  int fus_rk_close_shared_##SFX(fus_halo_t* halo, int variant, int put_next, T* u, T* v, T* u0,  \
-                                T* v0, T* ku, T* un, T* b, T* m, const T* m0, const T* m2,       \
-                                const T* m5, T bdt, T adt_next, int next_mode, void* s) {        \
-    return close_shared_entry<T>(halo, variant, put_next, u, v, u0, v0, ku, un, b, m, m0, m2,    \
-                                 m5, bdt, adt_next, next_mode, s);                               \
+  int fus_rk_close_shared_##SFX(fus_halo_t* halo, int variant, int put_next, int gather, T* u,   \
+                                T* v, T* u0, T* v0, T* ku, T* un, T* b, T* m, const T* m0,       \
+                                const T* m2, const T* m5, T bdt, T adt_next, int next_mode,      \
+                                void* s) {                                                       \
+    return close_shared_entry<T>(halo, variant, put_next, gather, u, v, u0, v0, ku, un, b, m,    \
+                                 m0, m2, m5, bdt, adt_next, next_mode, s);                       \
   }                                                                                              \
   int fus_rk_close_westervelt_##SFX(T* u, T* v, T* u0, T* v0, T* ku, T* kv, T* un, T* b, T* m,   \
                                     const T* m0, T bdt, T adt_next, int next_mode, int64_t n,    \
@@ -469,11 +497,11 @@ extern "C" {
   int fus_boundary_terms_signal_##SFX(fus_halo_t* halo, T* b, const T* vn, const int32_t* dof,   \
                                       const T* src, const T* src2, const T* absb, T g, T dg,     \
                                       const T* gtab, const int64_t* step_dev, int gstride,       \
-                                      int goff, int64_t n, void* s) {                            \
+                                      int goff, int64_t n, int consume_forward, void* s) {       \
     if (halo == nullptr)                                                                         \
       return fus_set_error(FUS_ERR_BAD_ARGUMENT, "boundary_terms_signal: null halo handle");     \
     return boundary_entry<T>(b, vn, dof, src, src2, absb, g, dg, gtab, step_dev, gstride, goff,  \
-                             n, s, halo);                                                        \
+                             n, s, halo, consume_forward);                                       \
   }
 
 FUS_RK_API(f64, double)

@@ -3,7 +3,7 @@
 // Each translation unit gets its own copy of the __constant__ derivative tables.
 #pragma once
 
-#include "fus_common.cuh"
+#include "halo_internal.cuh"
 
 namespace {
 
@@ -112,8 +112,23 @@ struct StiffArgs {
   const T* detJc;
   long long ncells;
   int bulk_ok;  // G base aligned for the 2-element vector loads of the AoS records
+  // multi-GPU (WAIT instantiations): cells [wait_from, ncells) of this launch touch ghost dofs.
+  // Before a CTA gathers for its first such batch it waits until every owner of this rank's ghosts
+  // has raised its FWD epoch (their halo put has landed): the forward exchange overlaps the
+  // interior cells of the SAME launch, no second launch, no second pipeline fill and drain.
+  const unsigned long long* wait_row;  // this rank's FWD flag row
+  const int* wait_src;                 // owner ranks
+  int wait_nsrc;
+  unsigned long long* wait_ctr;        // the handle's counters (FUS_CTR_FWD_WAITED is read, never written here)
+  long long wait_from;
 };
 
+// Gathers of x in a WAIT instantiation.  While a CTA works on interior cells it reads owned dofs
+// only and uses the read-only path (__ldg, LDG.CONSTANT - measured 3 % faster for this gather than
+// plain loads).  The neighbours write the ghost entries of x while the kernel runs, so once the
+// CTA has passed the halo wait every gather goes to L2 (__ldcg): a line cached in L1 before the
+// put landed (an interior cell gathering the owned dofs next to the first ghost entry) can never
+// be served.  Interface cells are a few per cent of the cells.
 template <typename T>
 struct G6 {
   T g0, g1, g2, g3, g4, g5;
@@ -146,7 +161,7 @@ __device__ __forceinline__ G6<float> load_g6(const float* p) {
 //   constant 1-D stiffness matrix K1 = D^T diag(w1) D - one n x n product per pencil and
 //   direction, the y / z pencils are transformed in place (8 tile passes instead of 16, two
 //   barriers instead of five).
-template <typename T, int n, int MODE, bool ATOMIC, int GEO>
+template <typename T, int n, int MODE, bool ATOMIC, int GEO, bool WAIT>
 __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
     stiffness_kernel(const StiffArgs<T> a) {
   constexpr bool AFF = GEO >= 1;
@@ -243,6 +258,8 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
       for (int i = 0; i < n; ++i) dof[i] = -1;
     }
   };
+  bool waited = false;  // WAIT: this CTA has passed the halo wait (CTA-uniform)
+  (void)waited;
   auto load_x = [&](const int (&dof)[n], T (&xa)[n], T (&xb)[n]) {
 #pragma unroll
     for (int i = 0; i < n; ++i) {
@@ -251,6 +268,34 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
       if (dof[i] >= 0) {
         xa[i] = __ldg(a.xa + dof[i]);
         if constexpr (DUAL) xb[i] = __ldg(a.xb + dof[i]);
+      }
+    }
+  };
+  auto load_x_l2 = [&](const int (&dof)[n], T (&xa)[n], T (&xb)[n]) {
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      xa[i] = T(0);
+      if constexpr (DUAL) xb[i] = T(0);
+      if (dof[i] >= 0) {
+        xa[i] = __ldcg(a.xa + dof[i]);
+        if constexpr (DUAL) xb[i] = __ldcg(a.xb + dof[i]);
+      }
+    }
+  };
+  // WAIT: called (by every thread of the CTA) before the x gather of batch `bx`
+  unsigned long long expect = 0;
+  long long b_wait = 0;
+  (void)expect;
+  (void)b_wait;
+  if constexpr (WAIT) {
+    expect = a.wait_ctr[FUS_CTR_FWD_WAITED] + 1ULL;
+    b_wait = a.wait_from / B;  // first batch holding an interface cell
+  }
+  auto halo_wait = [&](long long bx) {
+    if constexpr (WAIT) {
+      if (!waited && bx >= b_wait) {
+        fus_wait_flags(a.wait_row, a.wait_src, a.wait_nsrc, expect, a.wait_ctr);
+        waited = true;
       }
     }
   };
@@ -317,7 +362,12 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
   }
   load_dofs(blockIdx.x, dof);
   load_dofs(blockIdx.x + stride, dofn);
-  load_x(dof, xv, xw);
+  halo_wait(blockIdx.x);
+  if (WAIT && waited) {
+    load_x_l2(dof, xv, xw);
+  } else {
+    load_x(dof, xv, xw);
+  }
   if constexpr (WEST && !AFF) load_detj(blockIdx.x, reinterpret_cast<T(&)[n]>(dj));
 
   int it = 0;
@@ -363,7 +413,12 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
     // in flight during this whole batch: the dofmap entries of the batch after
     // next and the x pencil of the next batch (its entries arrived a batch ago)
     load_dofs(bn + stride, dofm);
-    load_x(dofn, xvn, xwn);
+    if (bn < nb) halo_wait(bn);
+    if (WAIT && waited) {
+      load_x_l2(dofn, xvn, xwn);
+    } else {
+      load_x(dofn, xvn, xwn);
+    }
     if constexpr (WEST && !AFF) load_detj(bn, reinterpret_cast<T(&)[n]>(djn));
     load_cell_scalars(bn, cscn);
 
@@ -574,24 +629,55 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
   }
 }
 
-template <typename T, int n, int MODE, bool ATOMIC, int GEO>
-int launch_cfg(const StiffArgs<T>& a, cudaStream_t stream) {
+template <typename T, int n, int MODE, bool ATOMIC, int GEO, bool WAIT>
+int launch_one(const StiffArgs<T>& a, cudaStream_t stream) {
   using L = Layout<T, n>;
   constexpr int SMEM = GEO ? L::SMEM_AFF : L::SMEM;
-  auto kern = stiffness_kernel<T, n, MODE, ATOMIC, GEO>;
-  static int blocks_per_sm = 0;  // per instantiation
-  if (blocks_per_sm == 0) {
+  auto kern = stiffness_kernel<T, n, MODE, ATOMIC, GEO, WAIT>;
+  // per instantiation AND per device: the shared-memory opt-in is a per-device attribute
+  static int blocks_per_sm[64] = {0};
+  int dev = 0;
+  FUS_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "stiffness: device index >= 64");
+  if (blocks_per_sm[dev] == 0) {
     FUS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     int occ = 0;
     FUS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg<T, n>::THREADS, SMEM));
-    blocks_per_sm = occ > 0 ? occ : 1;
+    blocks_per_sm[dev] = occ > 0 ? occ : 1;
   }
   const long long nb = (a.ncells + L::B - 1) / L::B;
-  long long grid = (long long)fus_num_sms() * blocks_per_sm;
+  long long grid = (long long)fus_num_sms() * blocks_per_sm[dev];
   if (grid > nb) grid = nb;
   kern<<<(unsigned)grid, Cfg<T, n>::THREADS, SMEM, stream>>>(a);
   FUS_LAUNCH_CHECK("stiffness_kernel");
   return 0;
+}
+
+template <typename T, int n, int MODE, bool ATOMIC, int GEO>
+int launch_cfg(StiffArgs<T> a, cudaStream_t stream) {
+  // a halo wait armed by fus_stiffness_arm_halo_wait applies to this launch (and is consumed)
+  const FusHaloDev* hd = nullptr;
+  long long from = 0;
+  a.wait_row = nullptr;
+  a.wait_src = nullptr;
+  a.wait_nsrc = 0;
+  a.wait_ctr = nullptr;
+  a.wait_from = a.ncells;
+  if (fus_take_armed_wait(&hd, &from)) {
+    if constexpr (ATOMIC) {
+      if (hd->n_owner_ranks > 0 && from < a.ncells) {
+        a.wait_row = hd->pad + (long long)FUS_ROW_FWD * hd->world;
+        a.wait_src = hd->owner_ranks;
+        a.wait_nsrc = hd->n_owner_ranks;
+        a.wait_ctr = hd->ctr;
+        a.wait_from = from < 0 ? 0 : from;
+        return launch_one<T, n, MODE, ATOMIC, GEO, true>(a, stream);
+      }
+    } else {
+      return fus_set_error(FUS_ERR_BAD_ARGUMENT, "stiffness: a halo wait cannot be combined with FUS_NO_ATOMICS");
+    }
+  }
+  return launch_one<T, n, MODE, ATOMIC, GEO, false>(a, stream);
 }
 
 template <typename T, int MODE, int GEO>

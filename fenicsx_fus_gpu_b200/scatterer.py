@@ -635,6 +635,23 @@ class P2PHaloExchange:
         check(fn("fus_halo_get_add", self.dtype)(self._h, self._vecs(vecs), len(vecs), current_stream()),
               "fus_halo_get_add")
 
+    def wait_reverse(self):
+        """Wait (one warp) for every ghosting neighbour's REV epoch - followed by a kernel that
+        gathers their partial sums itself (the solvers' fused close of the shared dofs)."""
+        self.fabric.host_sync()
+        check(self._lib.fus_halo_wait_reverse(self._h, current_stream()), "fus_halo_wait_reverse")
+
+    def arm_stiffness_wait(self, first_interface_cell):
+        """The next stiffness launch of this thread waits in-kernel, before its first interface
+        batch, for the puts of every owner of my ghosts (``fus_stiffness_arm_halo_wait``).
+        (Emulated ranks: call ``sync_point()`` once before the stage's launches.)"""
+        check(self._lib.fus_stiffness_arm_halo_wait(self._h, int(first_interface_cell)), "fus_stiffness_arm_halo_wait")
+
+    def sync_point(self):
+        """Emulated ranks only (one shared stream): every rank has enqueued its signalling kernels
+        before anybody enqueues a kernel that waits for them.  Nothing on real GPUs."""
+        self.fabric.host_sync()
+
     def barrier(self):
         """Neighbour barrier on the current stream (a host barrier when the ranks are emulated
         on one stream, where a waiting kernel would block the kernel it waits for)."""

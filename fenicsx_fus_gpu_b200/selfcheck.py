@@ -42,7 +42,7 @@ def _solver(su, workload, **kw):
 
 
 def multi_gpu_parity(P=4, n_per_rank=6, dtype=np.float64, nsteps=8, workload="linear", halo_kind="p2p",
-                     use_graph=True, geometry="stream", perturb=0.1, split_cells=True, group=None):
+                     use_graph=True, geometry="stream", perturb=0.1, split_cells=True, split_mode="none", group=None):
     """rel-L2 of the partitioned solve against the single-GPU solve of the same global box.
 
     Collective over ``group`` (default: world).  Returns a dict on every rank
@@ -63,6 +63,7 @@ def multi_gpu_parity(P=4, n_per_rank=6, dtype=np.float64, nsteps=8, workload="li
     su = problem.box_setup(P, ncells, lengths, dtype, rank, world, comm=group, grid=grid, perturb=perturb, seed=7,
                            halo_kind=halo_kind)
     sol = _solver(su, workload, split_cells=split_cells, **kw)
+    sol.split_mode = split_mode
     sol.init()
     sol.rk4(0.0, dt, nsteps)
     torch.cuda.synchronize()
@@ -73,7 +74,7 @@ def multi_gpu_parity(P=4, n_per_rank=6, dtype=np.float64, nsteps=8, workload="li
     parts = [None] * world
     dist.all_gather_object(parts, mine, group=group)
     out = dict(workload=workload, degree=P, dtype=dtype.name, n_gpus=world, global_cells=list(ncells),
-               global_dofs=int(su.global_dofs), steps=nsteps, halo=halo_kind, geometry=geometry,
+               global_dofs=int(su.global_dofs), steps=nsteps, halo=halo_kind, geometry=geometry, split_mode=split_mode,
                graph=bool(use_graph and sol._graph is not None), interface_cells=int(sol.ninterface),
                shared_dofs=int(getattr(sol.halo, "nshared", 0)), tol=TOL[dtype])
     res = [0.0, 0.0, 0.0]

@@ -29,11 +29,15 @@ replay needs no host work at all.
 Multi-GPU (peer-memory halo, ``scatterer.P2PHaloExchange``): the cells are split at set-up
 into *interior* ones and *interface* ones (those touching a ghost dof), and a stage becomes
 
-    main stream                                   exchange stream
-    interior cells                          ||    wait for the neighbours' puts; clear ghost b
-    interface cells, boundary terms, "my ghost sums are ready" signal
-    close on the dofs nobody shares         ||    get_add (ghost sums -> owners), close on the
-                                                  shared dofs + put of the next stage input
+    main stream                                        exchange stream
+    one-warp wait for the neighbours' puts (they were
+      issued beside the previous close: no stall)
+    stiffness (split_mode "two" / "fused": interior
+      cells first, the wait only before the interface cells)
+    boundary terms (+ "my ghost sums are ready" signal)
+    close on the dofs nobody shares               ||   one-warp wait for the neighbours' signals;
+                                                       ONE kernel: gather their ghost sums, close
+                                                       the shared dofs, put the next stage input
 
 so neither the forward nor the reverse exchange of cuda/demo_linear_box.py:536-553 is ever
 waited for on the critical path, and there is no barrier: the ordering is per-neighbour
@@ -55,8 +59,10 @@ from . import _lib
 from ._lib import check, current_stream, fn
 
 # a contiguous range of (permuted) cells that one kernel launch covers:
-# kind 0 rectilinear, 1 affine, 2 streamed G; c0/n cell range; g0 first row of the streamed G / detJ arrays
-Seg = namedtuple("Seg", "kind c0 n g0")
+# kind 0 rectilinear, 1 affine, 2 streamed G; c0/n cell range; g0 first row of the streamed G / detJ
+# arrays; ninterior: the first ninterior cells of the range touch no ghost dof (peer-memory halo: the
+# launch waits for the forward exchange only before its remaining, interface, cells)
+Seg = namedtuple("Seg", "kind c0 n g0 ninterior")
 
 A_RUNGE = (0.0, 0.5, 0.5, 1.0)
 B_RUNGE = (1.0 / 6.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0)
@@ -146,6 +152,17 @@ class _RK4:
         # peer-memory halo: launch interior cells (no ghost dof) while the forward exchange is in
         # flight and interface cells after it (False: one launch after the exchange, for A/B runs)
         self.split_cells = bool(split_cells)
+        # How a stage's stiffness launches wait for the forward exchange (measured on 2 and 8 B200s,
+        # profiles/r02_multigpu_timeline.md):
+        #   "none"  (default) a one-warp wait kernel, then every cell in one launch.  The neighbours'
+        #           put of stage i+1 is issued beside the ~0.5 ms close of stage i, so in steady state
+        #           the wait returns at once; fastest.
+        #   "two"   interior cells in one launch, interface cells (waiting first) in a second one:
+        #           a whole stage of slack against a late neighbour, for a second pipeline fill/drain.
+        #   "fused" one launch, every CTA waits in-kernel before its first interface batch: the
+        #           conditional barrier in the persistent loop stops the compiler from hoisting the
+        #           prefetch loads, which costs more (+25 us per launch) than the second launch.
+        self.split_mode = "none"
         self.nupd = int(halo.N) if self.p2p else self.ndofs  # entries the vector kernels update
         zx = halo.alloc if self.p2p else z
         # the reference's 14 vectors (cuda/demo_linear_box.py:380-385, 464-471)
@@ -183,9 +200,8 @@ class _RK4:
         self.Gc = self.detJc = None
         self._rect_tables = None
         self.cell_perm = None
-        # cell ranges per launch phase: "all" on one GPU / with the NCCL halo; "interior" (no ghost
-        # dof) and "interface" with the peer-memory halo, whose exchange overlaps the interior cells
-        self._phases = {"all": [Seg(2, 0, self.ncells, 0)]}
+        # cell ranges, one launch each (per geometry kind; interior cells first inside a range)
+        self._segs = [Seg(2, 0, self.ncells, 0, self.ncells)]
         self.ninterface = 0
 
     # the solution between steps (device tensors; write initial data into them before rk4)
@@ -283,7 +299,7 @@ class _RK4:
             self.ninterface = int(iface.sum().item())
         else:
             iface = torch.zeros(nc, dtype=torch.bool, device="cuda")
-        key = iface.to(torch.int32) * 3 + kind
+        key = kind * 2 + iface.to(torch.int32)  # rect [interior | interface], affine [..], streamed [..]
         counts = torch.bincount(key, minlength=6).cpu().tolist()
         if not bool((key[1:] >= key[:-1]).all().item()):
             perm = torch.argsort(key, stable=True)  # original order kept inside every range
@@ -293,7 +309,7 @@ class _RK4:
                 setattr(self, name, getattr(self, name)[perm].contiguous())
             if Gc is not None:
                 Gc, detJc = Gc[perm], detJc[perm]
-            rows = perm[key[perm] % 3 == 2] if self.naff else perm
+            rows = perm[kind[perm] == 2] if self.naff else perm
             self.G = self.G[rows].contiguous() if rows.numel() else None
             if detJ is not None:
                 self.detJ = detJ[rows].contiguous() if rows.numel() else None
@@ -305,19 +321,15 @@ class _RK4:
         if self.naff:
             self.Gc = Gc.contiguous()
             self.detJc = detJc.contiguous() if detJ is not None else None
-        # launch ranges
-        segs, c0, g0 = {0: [], 1: []}, 0, 0
-        for ph in (0, 1):
-            for k in (0, 1, 2):
-                n = counts[ph * 3 + k]
-                if n:
-                    segs[ph].append(Seg(k, c0, n, g0))
-                c0 += n
-                if k == 2:
-                    g0 += n
-        self._phases = {"all": segs[0] + segs[1]}
-        if split:
-            self._phases["interior"], self._phases["interface"] = segs[0], segs[1]
+        # launch ranges: one per geometry kind
+        self._segs, c0, g0 = [], 0, 0
+        for k in (0, 1, 2):
+            nint, nif = counts[2 * k], counts[2 * k + 1]
+            if nint + nif:
+                self._segs.append(Seg(k, c0, nint + nif, g0, nint if split else nint + nif))
+            c0 += nint + nif
+            if k == 2:
+                g0 += nint + nif
 
     # ---- stage pieces --------------------------------------------------------
     def _probed(self, launch):
@@ -336,7 +348,7 @@ class _RK4:
     def _ptr(self, t):
         return None if t is None else t.data_ptr()
 
-    def _boundary(self, stage, g, dg, use_table, vn, signal=False):
+    def _boundary(self, stage, g, dg, use_table, vn, signal=False, consume=False):
         """b += g*src + dg*src2 + vn*absb on the boundary dofs.  ``signal`` (peer-memory halo): the
         launch also raises the "ghost sums complete" epoch (and happens even without boundary dofs)."""
         nb = int(self._bdofs.numel())
@@ -347,7 +359,8 @@ class _RK4:
                 self.gtab.data_ptr() if use_table else None,
                 self.step_dev.data_ptr() if use_table else None, 8, 2 * stage, nb, current_stream())
         if signal:
-            check(fn("fus_boundary_terms_signal", self.dtype)(self.halo.handle, *args), "fus_boundary_terms_signal")
+            check(fn("fus_boundary_terms_signal", self.dtype)(self.halo.handle, *args[:-1], int(consume), args[-1]),
+                  "fus_boundary_terms_signal")
         else:
             check(fn("fus_boundary_terms", self.dtype)(*args), "fus_boundary_terms")
 
@@ -361,7 +374,7 @@ class _RK4:
             self.halo.barrier()  # nobody's first put may land before this rank is set up
         self._opened = True
 
-    def _assemble(self, stage, g, dg, use_table, x, vn, phase="all"):  # pragma: no cover - abstract
+    def _assemble(self, stage, g, dg, use_table, x, vn, wait=False):  # pragma: no cover - abstract
         raise NotImplementedError
 
     def _close(self, stage, dt, count_step, base, acc, skip=None):  # pragma: no cover - abstract
@@ -373,6 +386,29 @@ class _RK4:
     def _sptr(self, t, row):
         """Device address of row ``row`` of a per-cell tensor (no view objects on the launch path)."""
         return t.data_ptr() + int(row) * t.stride(0) * t.element_size()
+
+    def _launches(self, wait):
+        """(range, armed first-interface cell or None) per launch of a stage.  Peer-memory halo: a
+        launch waits in-kernel, before its first interface batch, for the neighbours' puts (without
+        the cell split: before its first batch); ``split_mode == "two"`` launches the interior cells
+        unarmed and the interface cells armed from their first batch."""
+        out = []
+        for sg in self._segs:
+            if not wait:
+                out.append((sg, None))
+            elif not self.split_cells:
+                out.append((sg, 0))
+            elif self.split_mode == "two" and 0 < sg.ninterior < sg.n:
+                out.append((Seg(sg.kind, sg.c0, sg.ninterior, sg.g0, sg.ninterior), None))
+                g1 = sg.g0 + (sg.ninterior if sg.kind == 2 else 0)
+                out.append((Seg(sg.kind, sg.c0 + sg.ninterior, sg.n - sg.ninterior, g1, 0), 0))
+            else:
+                out.append((sg, sg.ninterior if sg.ninterior < sg.n else None))
+        return out
+
+    def _arm(self, first):
+        if first is not None:
+            self.halo.arm_stiffness_wait(first)
 
     def _enqueue_step(self, dt, t, use_table, parity=None):
         """The launches of one RK4 step whose base state is ``_uv[parity]`` (default: the current
@@ -400,33 +436,39 @@ class _RK4:
 
     def _enqueue_step_p2p(self, dt, t, use_table, base, acc):
         """One RK4 step with the peer-memory halo overlapped with compute (module docstring).
-        Ordering across GPUs: every wait depends only on signals the neighbours raise from
-        kernels that are stream-ordered after kernels of EARLIER phases of this rank, so the
-        step can be captured and replayed as a graph without deadlock; the FWD epoch of stage
-        i+1 is raised after the neighbour's get_add of stage i, so it also frees the ghost
-        accumulators for clearing (see csrc/halo.cu)."""
+
+        Per stage, main stream: a one-warp wait for the neighbours' puts (issued beside the
+        previous stage's close, so normally long since landed; ``split_mode`` selects the variants
+        that launch the interior cells before waiting); the stiffness launches; the boundary
+        terms, whose last block signals "my ghost sums are complete"; the close on the dofs nobody
+        shares.  Exchange stream, beside that close: a one-warp wait for the neighbours' signals,
+        then ONE kernel that gathers their ghost sums, closes the shared dofs and puts the next
+        stage input into the neighbours' ghost slots.
+
+        Ordering across GPUs: every wait depends only on signals the neighbours raise from kernels
+        that are stream-ordered after kernels of EARLIER phases of this rank, so the step can be
+        captured and replayed as a graph without deadlock.  A neighbour's put of stage i+1 is
+        issued by the kernel that gathered (and cleared) my ghost sums of stage i, so its FWD epoch
+        also says the ghost accumulators are clean."""
         h = self.halo
-        accum = (self.b, self.m) if self._m_accum else (self.b,)
-        interior = "interior" if "interior" in self._phases else None
-        # the stage-0 input (the base state) is already on its way to the neighbours' ghost
-        # slots: put there by begin_steps() or by the last stage of the previous step
         for i in range(4):
             g = dg = 0.0
             if not use_table and self.source is not None:
                 g, dg = self.source(t + C_RUNGE[i] * dt if self.source_at_stage_time else t)
+            # the stage input is on its way to (or already in) the ghost slots: put there by
+            # begin_steps() or by the previous stage's close of the shared dofs
             x, vn = base if i == 0 else (self.un, self.ku)
+            in_kernel = self.split_cells and self.split_mode in ("two", "fused")
+            if in_kernel:
+                h.sync_point()
+            else:
+                h.wait_forward()
+            self._assemble(i, g, dg, use_table, x, vn, wait=in_kernel)
+            self._boundary(i, g, dg, use_table, vn, signal=True, consume=in_kernel)
             h.fork()
             with h.side():
-                h.wait_forward(*accum)  # ghost values of (x, vn) have landed; ghost sums cleared
-            if interior:
-                self._assemble(i, g, dg, use_table, x, vn, "interior")
-            h.join()
-            self._assemble(i, g, dg, use_table, x, vn, "interface" if interior else "all")
-            self._boundary(i, g, dg, use_table, vn, signal=True)  # + "my ghost sums are complete"
-            h.fork()
-            with h.side():
-                h.get_add(*accum)
-                self._close_shared(i, dt, base, acc)  # + put of the next stage's / next step's input
+                h.wait_reverse()
+                self._close_shared(i, dt, base, acc)
             self._close(i, dt, use_table, base, acc, skip=h.shared_mask)
             h.join()
 
@@ -623,11 +665,12 @@ class LinearSpectral3D(_RK4):
         self._boundary_setup(terms)
         self._setup_geometry(None, ["cell_coeff2"])
 
-    def _stiffness(self, x=None, phase="all"):
+    def _stiffness(self, x=None, wait=False):
         x = self.un if x is None else x
         st, xp, bp, sp = current_stream(), x.data_ptr(), self.b.data_ptr(), self._sptr
-        for sg in self._phases[phase]:
+        for sg, first in self._launches(wait):
             cf, dm = sp(self.cell_coeff2, sg.c0), sp(self.dofmap, sg.c0)
+            self._arm(first)
             if sg.kind == 0:  # rectilinear cells: three decoupled 1-D stiffness products
                 check(fn("fus_stiffness_rect", self.dtype)(
                     xp, cf, bp, sp(self.Gc, sg.c0), dm, None, sg.n, self.P, FUS_TABLES_RESIDENT, st),
@@ -641,9 +684,9 @@ class LinearSpectral3D(_RK4):
                     xp, cf, bp, sp(self.G, sg.g0), dm, None, sg.n, self.P, FUS_TABLES_RESIDENT, st),
                     "fus_stiffness")
 
-    def _assemble(self, stage, g, dg, use_table, x, vn, phase="all"):
+    def _assemble(self, stage, g, dg, use_table, x, vn, wait=False):
         # b += K(-1/rho; un)                                  (cuda/demo_linear_box.py:543-545)
-        self._probed(lambda: self._stiffness(x, phase))
+        self._probed(lambda: self._stiffness(x, wait))
 
     def _close(self, stage, dt, count_step, base, acc, skip=None):
         u, v, u0, v0, bdt, adt, mode = self._close_args(stage, dt, base, acc)
@@ -655,7 +698,7 @@ class LinearSpectral3D(_RK4):
     def _close_shared(self, stage, dt, base, acc):
         u, v, u0, v0, bdt, adt, mode = self._close_args(stage, dt, base, acc)
         check(fn("fus_rk_close_shared", self.dtype)(
-            self.halo.handle, 0, 1, u, v, u0, v0, self.ku.data_ptr(), self.un.data_ptr(),
+            self.halo.handle, 0, 1, 1, u, v, u0, v0, self.ku.data_ptr(), self.un.data_ptr(),
             self.b.data_ptr(), self.m.data_ptr(), None, None, None, bdt, adt, mode, current_stream()),
             "fus_rk_close_shared")
 
@@ -733,19 +776,20 @@ class WesterveltSpectral3D(_RK4):
     def _state(self):
         return super()._state() + [self.m0]
 
-    def _assemble(self, stage, g, dg, use_table, x, vn, phase="all"):
+    def _assemble(self, stage, g, dg, use_table, x, vn, wait=False):
         # b += K(c3; un) + K(c4; vn) [+ M(c5; vn^2) and m += M(c2; un)]: ONE pass over G (, detJ)
         # and the dofmap, un / vn gathered once                    (:609-612, :620-628)
-        self._probed(lambda: self._stage_kernel(x, vn, phase))
+        self._probed(lambda: self._stage_kernel(x, vn, wait))
 
-    def _stage_kernel(self, x=None, vn=None, phase="all"):
+    def _stage_kernel(self, x=None, vn=None, wait=False):
         x = self.un if x is None else x
         vn = self.ku if vn is None else vn
         st, sp, P, R = current_stream(), self._sptr, self.P, FUS_TABLES_RESIDENT
         xp, vp, bp = x.data_ptr(), vn.data_ptr(), self.b.data_ptr()
-        for sg in self._phases[phase]:
+        for sg, first in self._launches(wait):
             c0 = sg.c0
             c3, c4, dm = sp(self.c3, c0), sp(self.c4, c0), sp(self.dofmap, c0)
+            self._arm(first)
             if not self._m_accum:
                 # b += K(c3; un) + K(c4; vn): the dual stiffness action, one pass over G
                 if sg.kind == 0:
@@ -790,7 +834,7 @@ class WesterveltSpectral3D(_RK4):
         u, v, u0, v0, bdt, adt, mode = self._close_args(stage, dt, base, acc)
         pw = not self._m_accum
         check(fn("fus_rk_close_shared", self.dtype)(
-            self.halo.handle, 2 if pw else 1, 1, u, v, u0, v0, self.ku.data_ptr(), self.un.data_ptr(),
+            self.halo.handle, 2 if pw else 1, 1, 1, u, v, u0, v0, self.ku.data_ptr(), self.un.data_ptr(),
             self.b.data_ptr(), None if pw else self.m.data_ptr(), self.m0.data_ptr(),
             self.m2.data_ptr() if pw else None, self.m5.data_ptr() if pw else None, bdt, adt, mode,
             current_stream()), "fus_rk_close_shared")

@@ -306,9 +306,24 @@ int fus_halo_put_f32(fus_halo_t* h, float* const* vecs, int nvec, void* stream);
 int fus_halo_wait_forward_f64(fus_halo_t* h, double* const* zero_vecs, int nzero, void* stream);
 int fus_halo_wait_forward_f32(fus_halo_t* h, float* const* zero_vecs, int nzero, void* stream);
 int fus_halo_signal_reverse(fus_halo_t* h, void* stream);
+/* wait (one warp) for the REV epoch of every ghosting neighbour - the first half of get_add, for
+ * callers that fuse the gather into their own kernel (fus_rk_close_shared_* with gather != 0) */
+int fus_halo_wait_reverse(fus_halo_t* h, void* stream);
 int fus_halo_get_add_f64(fus_halo_t* h, double* const* vecs, int nvec, void* stream);
 int fus_halo_get_add_f32(fus_halo_t* h, float* const* vecs, int nvec, void* stream);
 int fus_halo_barrier(fus_halo_t* h, void* stream);
+
+/* Forward halo overlapped with the interior cells INSIDE one stiffness launch.  Arms the NEXT
+ * fus_stiffness* / fus_stiffness2* / fus_stiffness_westervelt* (streamed, affine or rectilinear)
+ * launch issued by this host thread: cells [first_interface_cell, ncells) of that launch are the
+ * ones that touch ghost dofs (the caller orders interior cells first).  Every CTA of the persistent
+ * kernel works through its interior batches first and, before gathering for its first interface
+ * batch, waits for the FWD epoch of every owner of this rank's ghosts (what fus_halo_wait_forward
+ * would wait for); from then on it gathers x through L2.  The epoch is consumed by the
+ * fus_boundary_terms_signal_* launch that follows (consume_forward != 0).  halo == NULL disarms.
+ * Replaces scatter_forward(u_n), scatter_forward(v_n) -> stiffness of cuda/demo_linear_box.py:536-545
+ * without a second launch for the interface cells.  Not combinable with FUS_NO_ATOMICS. */
+int fus_stiffness_arm_halo_wait(const fus_halo_t* halo, int64_t first_interface_cell);
 
 /* --------------------------------------------------------------------- *
  * Fused RK4 stage kernels.  Replace the 13 vector launches per stage of
@@ -360,16 +375,19 @@ int fus_rk_close_f32(float* u, float* v, float* u0, float* v0, float* ku, float*
  * in flight and this (small, indexed) kernel runs after fus_halo_get_add.  With put_next != 0 it is
  * fused with the forward halo of the NEXT stage: the fresh stage input (un, ku; or u, v in
  * next_mode 4) is stored straight into the neighbours' ghost slots, followed by the FWD epoch
- * (= fus_halo_put of those two vectors).  variant 0: fus_rk_close (m); 1: fus_rk_close_westervelt
+ * (= fus_halo_put of those two vectors).  With gather != 0 it is also fused with the reverse halo
+ * (call fus_halo_wait_reverse first): each thread adds the neighbours' ghost partial sums of its
+ * dof to b (and m, variant 1), loaded straight from their vectors, and clears them there - no
+ * get_add pass, no atomics, no kernel to zero the ghost accumulators.  variant 0: fus_rk_close (m); 1: fus_rk_close_westervelt
  * (m, m0); 2: fus_rk_close_westervelt_pw (m0, m2, m5); unused mass pointers may be NULL.
  * Replaces scatter_reverse(b) -> pointwise_divide/axpy -> (next stage) scatter_forward(un),
  * scatter_forward(vn) of cuda/demo_linear_box.py:536-563. */
-int fus_rk_close_shared_f64(fus_halo_t* halo, int variant, int put_next, double* u, double* v,
-                            double* u0, double* v0, double* ku, double* un, double* b, double* m,
-                            const double* m0, const double* m2, const double* m5, double bdt,
-                            double adt_next, int next_mode, void* stream);
-int fus_rk_close_shared_f32(fus_halo_t* halo, int variant, int put_next, float* u, float* v,
-                            float* u0, float* v0, float* ku, float* un, float* b, float* m,
+int fus_rk_close_shared_f64(fus_halo_t* halo, int variant, int put_next, int gather, double* u,
+                            double* v, double* u0, double* v0, double* ku, double* un, double* b,
+                            double* m, const double* m0, const double* m2, const double* m5,
+                            double bdt, double adt_next, int next_mode, void* stream);
+int fus_rk_close_shared_f32(fus_halo_t* halo, int variant, int put_next, int gather, float* u,
+                            float* v, float* u0, float* v0, float* ku, float* un, float* b, float* m,
                             const float* m0, const float* m2, const float* m5, float bdt,
                             float adt_next, int next_mode, void* stream);
 
@@ -392,15 +410,17 @@ int fus_boundary_terms_f32(float* b, const float* vn, const int32_t* dof, const 
 
 /* The same, followed by fus_halo_signal_reverse(halo) from the kernel's last block: in a multi-GPU
  * stage the boundary terms are the last writes into the ghost partial sums, so the "my sums are
- * complete" epoch rides on this launch instead of needing one of its own (n may be 0). */
+ * complete" epoch rides on this launch instead of needing one of its own (n may be 0).
+ * consume_forward != 0: also advance the "forward epochs waited for" counter - the stage's stiffness
+ * launches were armed with fus_stiffness_arm_halo_wait and have waited in-kernel. */
 int fus_boundary_terms_signal_f64(fus_halo_t* halo, double* b, const double* vn, const int32_t* dof,
                                   const double* src, const double* src2, const double* absb, double g,
                                   double dg, const double* gtab, const int64_t* step_dev, int gstride,
-                                  int goff, int64_t n, void* stream);
+                                  int goff, int64_t n, int consume_forward, void* stream);
 int fus_boundary_terms_signal_f32(fus_halo_t* halo, float* b, const float* vn, const int32_t* dof,
                                   const float* src, const float* src2, const float* absb, float g,
                                   float dg, const float* gtab, const int64_t* step_dev, int gstride,
-                                  int goff, int64_t n, void* stream);
+                                  int goff, int64_t n, int consume_forward, void* stream);
 
 /* Westervelt stage helpers (cuda/demo_nonlinear_bowl.py:603-650):
  *   w = vn*vn                                                   (:603)

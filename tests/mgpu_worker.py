@@ -88,6 +88,8 @@ def main():
         dict(workload="linear", P=4, n_per_rank=6, dtype="float64", nsteps=8),  # graph replay, overlap
         dict(workload="linear", P=4, n_per_rank=6, dtype="float64", nsteps=8, use_graph=False),
         dict(workload="linear", P=4, n_per_rank=6, dtype="float64", nsteps=8, split_cells=False),
+        dict(workload="linear", P=4, n_per_rank=6, dtype="float64", nsteps=8, split_mode="two"),
+        dict(workload="linear", P=4, n_per_rank=6, dtype="float64", nsteps=8, split_mode="fused"),
         dict(workload="linear", P=4, n_per_rank=6, dtype="float64", nsteps=8, halo_kind="nccl"),
         dict(workload="westervelt", P=4, n_per_rank=5, dtype="float64", nsteps=6),
     ]
@@ -97,6 +99,8 @@ def main():
             dict(workload="linear", P=4, n_per_rank=8, dtype="float64", nsteps=6, geometry="auto", perturb=0.0),
             dict(workload="piston", P=5, n_per_rank=4, dtype="float64", nsteps=6),
             dict(workload="westervelt_cells", P=3, n_per_rank=5, dtype="float64", nsteps=6),
+            dict(workload="westervelt_cells", P=3, n_per_rank=5, dtype="float64", nsteps=6, split_mode="fused"),
+            dict(workload="linear", P=4, n_per_rank=8, dtype="float64", nsteps=6, geometry="auto", perturb=0.0, split_mode="two"),
             dict(workload="westervelt", P=4, n_per_rank=5, dtype="float32", nsteps=6),
             dict(workload="westervelt", P=6, n_per_rank=3, dtype="float64", nsteps=4),
             dict(workload="linear", P=2, n_per_rank=9, dtype="float64", nsteps=8),
@@ -110,7 +114,7 @@ def main():
         results.append(r)
         if rank == 0:
             print(f"[mgpu] {r['workload']} P{r['degree']} {r['dtype']} halo={r['halo']} geometry={r['geometry']} "
-                  f"graph={r['graph']} iface={r['interface_cells']}: rel-L2 u {r['rel_l2_u']:.2e} v {r['rel_l2_v']:.2e} "
+                  f"graph={r['graph']} split={r['split_mode']} iface={r['interface_cells']}: rel-L2 u {r['rel_l2_u']:.2e} v {r['rel_l2_v']:.2e} "
                   f"{'ok' if r['ok'] else 'FAIL'}", flush=True)
     sc = scatter_cases(rank, world)
     allsc = [None] * world

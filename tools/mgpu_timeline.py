@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--n", type=int, default=80)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--split-mode", default="none")
     ap.add_argument("--fake-p2p", action="store_true",
                     help="1 GPU: a one-rank peer-memory halo (no neighbours) - vectors in the symmetric arena and the "
                          "skip mask passed to the close kernel, nothing exchanged: their cost in situ")
@@ -76,6 +77,7 @@ def main():
     else:
         solver, info = bench.build_problem(rank, world, a.n, np.float64, "p2p", "linear_box", 4, "stream")
     dt = info["dt"]
+    solver.split_mode = a.split_mode
     out["graph_ms_per_step"] = timed_graph(solver, dt, a.steps)
     out["graph_ms_per_step_again"] = timed_graph(solver, dt, a.steps)
     if world > 1:
@@ -104,12 +106,12 @@ def main():
 
         setattr(obj, name, g)
 
-    wrap(solver, "_assemble", lambda *x, **k: "stiffness:" + (x[6] if len(x) > 6 else "all"))
+    wrap(solver, "_assemble", "stiffness")
     wrap(solver, "_boundary", "boundary")
     wrap(solver, "_close", lambda *x, **k: f"close{'(masked)' if solver.p2p else ''}[stage {x[0]}]")
     if solver.p2p:
         wrap(solver, "_close_shared", "close_shared+put")
-        for nm in ("put", "wait_forward", "signal_reverse", "get_add", "barrier"):
+        for nm in ("put", "wait_forward", "wait_reverse", "barrier"):
             wrap(solver.halo, nm, "halo." + nm)
     solver.use_graph = False
     solver.init()
