@@ -89,7 +89,8 @@ class HaloDesc(C.Structure):
                 ("n_owner_ranks", C.c_int32), ("owner_ranks", C.c_void_p),
                 ("n", C.c_int64), ("idx", C.c_void_p), ("remote_pos", C.c_void_p), ("entry_seg", C.c_void_p),
                 ("size_local", C.c_int64), ("num_ghosts", C.c_int64),
-                ("signal_pad", C.c_void_p), ("peer_pad", C.c_void_p), ("peer_delta", C.c_void_p)]
+                ("signal_pad", C.c_void_p), ("peer_pad", C.c_void_p), ("peer_delta", C.c_void_p),
+                ("close_group", C.c_int32)]
 
 
 def exported_symbols():

@@ -268,9 +268,10 @@ int fus_halo_create(const fus_halo_desc_t* desc, fus_halo_t** out) {
   }
 
   // Entries grouped by owned dof.  The dofs fus_rk_close_* leaves to fus_rk_close_shared_* are the
-  // shared ones AND the other members of their aligned group of 4 (one float4 / two double2 packs
-  // of the vectorised close kernel), so that kernel can skip whole packs and needs no scalar
-  // path; the extra members have no ghost copies (an empty CSR row: closed, nothing put).
+  // shared ones AND the other members of their aligned group of `close_group` dofs (one pack of
+  // the vectorised close kernel: 2 doubles / 4 floats), so that kernel can skip whole packs and
+  // needs no scalar path (measured slower, even out of line); the extra members have no ghost
+  // copies (an empty CSR row: closed, nothing put).
   std::vector<int64_t> order(n);
   std::iota(order.begin(), order.end(), (int64_t)0);
   std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return desc->idx[a] < desc->idx[b]; });
@@ -281,9 +282,11 @@ int fus_halo_create(const fus_halo_desc_t* desc, fus_halo_t** out) {
     useg[k] = desc->entry_seg[order[k]];
     upos[k] = desc->remote_pos[order[k]];
   }
+  const long long grp = desc->close_group == 1 || desc->close_group == 2 ? desc->close_group : 4;
+  const long long gmask = ~(grp - 1);
   for (int64_t k = 0; k < n; ++k) {
-    if (k > 0 && (sorted_idx[k] & ~3LL) == (sorted_idx[k - 1] & ~3LL)) continue;  // group already listed
-    for (long long m = sorted_idx[k] & ~3LL; m < (sorted_idx[k] & ~3LL) + 4 && m < desc->size_local; ++m) uniq.push_back(m);
+    if (k > 0 && (sorted_idx[k] & gmask) == (sorted_idx[k - 1] & gmask)) continue;  // group already listed
+    for (long long m = sorted_idx[k] & gmask; m < (sorted_idx[k] & gmask) + grp && m < desc->size_local; ++m) uniq.push_back(m);
   }
   // CSR row of uniq[i]: the entries whose dof is uniq[i] (none for the non-shared group members)
   for (long long dd : uniq)

@@ -268,13 +268,20 @@ __global__ void __launch_bounds__(kThreads, 3) rk_close_kernel(const CloseArgs<T
 // (their b is complete only after the reverse halo), fused with the forward halo of the
 // NEXT stage: the fresh stage input (un, vn = ku; or the new state u, v after the last
 // stage) goes straight from registers into the neighbours' ghost slots, then the FWD epoch.
+// Runs BESIDE rk_close_kernel, which keeps 3 blocks of 256 threads x 80 registers resident per SM
+// (61k of the 64k registers).  Blocks of 64 threads fit into what is left, so this kernel starts at
+// once instead of waiting for close blocks to retire, and never displaces one: with 256-thread
+// blocks the close of the ranks that own shared faces took 530 us instead of 485 on 8 GPUs
+// (profiles/r02_multigpu_timeline.md).  Its threads mostly wait on remote loads; a small grid is enough.
+constexpr int kSharedThreads = 64;
+
 template <typename T, int WEST>
-__global__ void __launch_bounds__(kThreads) rk_close_shared_kernel(const CloseArgs<T> a, const FusHaloDev h, int put,
-                                                                   int gather) {
-  const long long stride = (long long)gridDim.x * kThreads;
+__global__ void __launch_bounds__(kSharedThreads) rk_close_shared_kernel(const CloseArgs<T> a, const FusHaloDev h, int put,
+                                                                         int gather) {
+  const long long stride = (long long)gridDim.x * kSharedThreads;
   T* const xa = a.next_mode == 4 ? a.u : a.un;
   T* const xb = a.next_mode == 4 ? a.v : a.ku;
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < h.nu; i += stride) {
+  for (long long i = (long long)blockIdx.x * kSharedThreads + threadIdx.x; i < h.nu; i += stride) {
     const long long k = h.uniq[i];
     const long long j0 = h.uoff[i], j1 = h.uoff[i + 1];
     if (gather && j1 > j0) {
@@ -416,17 +423,17 @@ int close_shared_entry(fus_halo* halo, int variant, int put_next, int gather, T*
   if (h.nu == 0) return 0;  // nothing shared: nobody ghosts my dofs, nobody waits for my signal
   CloseArgs<T> a{u, v, u0, v0, ku, nullptr, un, b, m, m0, m2, m5, bdt, adt_next, next_mode, h.size_local,
                  nullptr, nullptr};
-  long long blocks = (h.nu + kThreads - 1) / kThreads;
-  const long long cap = (long long)fus_num_sms() * 4;
+  long long blocks = (h.nu + kSharedThreads - 1) / kSharedThreads;
+  const long long cap = (long long)fus_num_sms() * 2;
   if (blocks > cap) blocks = cap;
   cudaStream_t st_ = static_cast<cudaStream_t>(stream);
   const int put = put_next ? 1 : 0, gat = gather ? 1 : 0;
   if (variant == 0) {
-    rk_close_shared_kernel<T, 0><<<(unsigned)blocks, kThreads, 0, st_>>>(a, h, put, gat);
+    rk_close_shared_kernel<T, 0><<<(unsigned)blocks, kSharedThreads, 0, st_>>>(a, h, put, gat);
   } else if (variant == 1) {
-    rk_close_shared_kernel<T, 1><<<(unsigned)blocks, kThreads, 0, st_>>>(a, h, put, gat);
+    rk_close_shared_kernel<T, 1><<<(unsigned)blocks, kSharedThreads, 0, st_>>>(a, h, put, gat);
   } else {
-    rk_close_shared_kernel<T, 2><<<(unsigned)blocks, kThreads, 0, st_>>>(a, h, put, gat);
+    rk_close_shared_kernel<T, 2><<<(unsigned)blocks, kSharedThreads, 0, st_>>>(a, h, put, gat);
   }
   FUS_LAUNCH_CHECK("rk_close_shared_kernel");
   return 0;

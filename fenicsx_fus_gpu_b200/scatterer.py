@@ -574,6 +574,7 @@ class P2PHaloExchange:
         d.size_local, d.num_ghosts = self.N, self.nghost
         d.signal_pad = self.pad.data_ptr()
         d.peer_pad, d.peer_delta = peer_pad.ctypes.data, peer_delta.ctypes.data
+        d.close_group = 16 // self.dtype.itemsize  # one 16-byte pack of the close kernel
         torch.cuda.synchronize()  # the pad is zeroed before the handle (and any neighbour) can use it
         h = C.c_void_p()
         check(lib.fus_halo_create(C.byref(d), C.byref(h)), "fus_halo_create")

@@ -262,6 +262,7 @@ typedef struct {
   void* signal_pad;           /* DEVICE my pad, fus_halo_pad_bytes(world) bytes, zeroed, peer-mapped */
   const uint64_t* peer_pad;   /* HOST [world] device address of rank q's pad as mapped HERE (0: unmapped) */
   const int64_t* peer_delta;  /* HOST [world] (rank q's arena base as mapped here) - (my arena base), bytes */
+  int32_t close_group;        /* dofs per pack of the close kernel that will take the mask: 2 (f64), 4 (f32; default) */
 } fus_halo_desc_t;
 
 int64_t fus_halo_pad_bytes(int world);
@@ -271,7 +272,7 @@ int64_t fus_halo_pad_bytes(int world);
 int fus_halo_create(const fus_halo_desc_t* desc, fus_halo_t** out);
 int fus_halo_destroy(fus_halo_t* h);
 /* The owned dofs fus_rk_close_shared_* closes - those that are ghosts somewhere plus the other
- * members of their aligned groups of 4 (so the vectorised close kernel skips whole packs) - and
+ * members of their aligned groups of `close_group` (so the vectorised close kernel skips whole packs) - and
  * the bitmask over [0, size_local) marking them (bit d%8 of byte d/8), which fus_rk_close_* takes
  * as skip_mask (DEVICE pointer). */
 int64_t fus_halo_num_shared(const fus_halo_t* h);

@@ -159,7 +159,7 @@ def test_p2p_halo_handle_vs_reference_fixture(golden_dir, name):
         assert np.array_equal(out[r][0], g[f"r{r}_fwd"])
         assert rel_l2(out[r][1], g[f"r{r}_rev"]) < 1e-15
         shared = np.unique(np.concatenate([np.zeros(0, np.int64)] + _lists(g, r, "ghosts")[0]))
-        assert shared.size <= out[r][2] <= 4 * shared.size  # shared dofs + the rest of their groups of 4
+        assert shared.size <= out[r][2] <= 2 * shared.size  # shared dofs + the rest of their 16-byte packs
 
 
 @pytest.mark.parametrize("P", range(2, 8))
