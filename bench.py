@@ -141,7 +141,7 @@ WORKLOADS = {
 
 
 def build_problem(rank, world, n_per_gpu, dtype, halo_kind, workload="linear_box", degree=None, geometry="stream",
-                  split_cells=True):
+                  split_cells=True, integrator="rk4"):
     """The demo's preamble through fenicsx_fus_gpu_b200.problem (device geometry,
     block partition, halo).  Returns the solver and an info dict."""
     from fenicsx_fus_gpu_b200 import problem
@@ -166,12 +166,13 @@ def build_problem(rank, world, n_per_gpu, dtype, halo_kind, workload="linear_box
     def make_solver(geometry="stream"):
         if workload == "linear_box":
             return problem.linear_solver(su, source_facets=[2], absorbing_facets=[3], rho=W["rho"], c0=W["c0"],
-                                         f0=W["f0"], p0=P0, geometry=geometry, split_cells=split_cells)
+                                         f0=W["f0"], p0=P0, geometry=geometry, split_cells=split_cells,
+                                         integrator=integrator)
         if workload == "linear_piston":
             piston = problem.disc(0, 1, (0.5 * lengths[0], 0.5 * lengths[1]), 0.01)
             return problem.linear_solver(
                 su, source_facets=[0], absorbing_facets=[0, 1, 2, 3, 4, 5], rho=W["rho"], c0=W["c0"], f0=W["f0"],
-                p0=P0, source_predicate=piston, geometry=geometry, split_cells=split_cells,
+                p0=P0, source_predicate=piston, geometry=geometry, split_cells=split_cells, integrator=integrator,
                 absorbing_predicate=lambda cen: ~(piston(cen) & (cen[:, 2] < 0.5 * h)))
         centre = (0.5 * lengths[1], 0.5 * lengths[2])
         return problem.westervelt_solver(
@@ -305,6 +306,8 @@ def main():
     ap.add_argument("--split-mode", default="none", choices=["none", "two", "fused"],
                     help="p2p halo: wait, then all cells in one launch (default); interface cells in a second launch; "
                          "or in the same launch behind an in-kernel wait (A/B, see solver.py)")
+    ap.add_argument("--integrator", default="rk4", choices=["rk4", "leapfrog"],
+                    help="rk4 (the reference's scheme, the headline) or leapfrog (one stiffness action per step)")
     ap.add_argument("--no-graph", action="store_true", help="launch the steps eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-kind", default=None, choices=["numba", "cpp", "port"], help="CPU arm implementation")
     ap.add_argument("--sustain-steps", type=int, default=250, help="steps of the extra >= 1 s sustained measurement")
@@ -332,6 +335,11 @@ def main():
               "degree": deg, "cells_per_gpu": n_per_gpu**3, "parallelism": f"block partition x{world}",
               "l2": "working set per GPU (G + dofmap + 9 vectors, GBs) >> 126 MB L2: no flush needed"}
     METRIC = "fused RK4 stage throughput (global dofs x stages / s)"
+    NST = 4  # stages (= operator applications) per step
+    if a.integrator == "leapfrog":
+        if a.workload == "nonlinear_bowl" or a.impl != "ours":
+            raise SystemExit("--integrator leapfrog: linear workloads of this repo only (the reference implements RK4)")
+        METRIC, NST = "fused leapfrog step throughput (global dofs x steps / s; one operator application per step)", 1
 
     if a.impl == "reference":
         # the reference's CPU implementation of the path on this box's host cores: the workload's
@@ -429,7 +437,8 @@ def main():
 
     log("building the problem")
     solver, info = build_problem(rank, world, n_per_gpu, dtype, a.halo, a.workload, deg, a.geometry,
-                                 split_cells=not a.no_split)
+                                 split_cells=not a.no_split, integrator=a.integrator)
+    config["integrator"] = a.integrator
     config["geometry"] = ("G streamed (reference data flow)" if a.geometry == "stream" else
                           f"auto: {solver.nrect} rectilinear + {solver.naff - solver.nrect} affine of {solver.ncells} "
                           "cells per GPU keep 6 geometric factors instead of 6 n^3")
@@ -470,7 +479,7 @@ def main():
     barrier()
     elapsed = maxr(e0.elapsed_time(e1) * 1e-3)
     gdofs_global = info["global_dofs"]
-    value = gdofs_global * 4 * a.steps / elapsed / 1e9
+    value = gdofs_global * NST * a.steps / elapsed / 1e9
     log(f"timed region done: {elapsed * 1e3 / a.steps:.3f} ms/step")
 
     # ---- sustained: the same steps for >= 1 s (the contract's K is short); the clocks are sampled
@@ -485,7 +494,7 @@ def main():
         barrier()
         el_s = maxr(e0.elapsed_time(e1) * 1e-3)
         sustained = {"steps": ns, "seconds": el_s, "ms_per_step": el_s / ns * 1e3,
-                     "value": gdofs_global * 4 * ns / el_s / 1e9, "unit": "GDoF/s"}
+                     "value": gdofs_global * NST * ns / el_s / 1e9, "unit": "GDoF/s"}
         log(f"sustained: {sustained['ms_per_step']:.3f} ms/step over {el_s:.2f} s")
     w1 = time.time()
     clk = clocks.stop(w0, w1)
@@ -512,7 +521,7 @@ def main():
     nprobe = min(a.steps, 10)
     solver.rk4(solver.t, dt, nprobe)
     torch.cuda.synchronize()
-    t_in_step = float(np.sum([e_a.elapsed_time(e_b) for e_a, e_b in solver.probe])) * 1e-3 / (4 * nprobe)
+    t_in_step = float(np.sum([e_a.elapsed_time(e_b) for e_a, e_b in solver.probe])) * 1e-3 / (NST * nprobe)
     n_probed = len(solver.probe)
     solver.probe = None
     solver.use_graph = not a.no_graph
@@ -555,7 +564,7 @@ def main():
     barrier()
     e2e_elapsed = maxr(max(e0.elapsed_time(e1) * 1e-3, 0.0))
     e2e_wall = maxr(time.perf_counter() - t0)
-    e2e_value = gdofs_global * 4 * a.steps / max(e2e_elapsed, e2e_wall) / 1e9
+    e2e_value = gdofs_global * NST * a.steps / max(e2e_elapsed, e2e_wall) / 1e9
     h2d = 8 * s
     d2h = nsample * s
 
@@ -647,7 +656,7 @@ def main():
     t_mass = float(np.mean([ea.elapsed_time(eb) for ea, eb in evm])) * 1e-3
     bytes_mass = nc * (nd3 * (4 + s) + s) + 2 * s * nd
     stage_bytes = solver.stage_bytes()
-    stage_t = elapsed / (4 * a.steps)
+    stage_t = elapsed / (NST * a.steps)
 
     # ---- the operator through the C ABI with HOST buffers (fus_stiffness_host_*): x from pinned
     #      host memory, y back to pinned host memory, both copies inside the call ----
@@ -691,7 +700,7 @@ def main():
         e1.record()
         barrier()
         el2 = maxr(e0.elapsed_time(e1) * 1e-3)
-        affine = {"value": gdofs_global * 4 * a.steps / el2 / 1e9, "unit": "GDoF/s", "ms_per_step": el2 / a.steps * 1e3,
+        affine = {"value": gdofs_global * NST * a.steps / el2 / 1e9, "unit": "GDoF/s", "ms_per_step": el2 / a.steps * 1e3,
                   "steps_per_s": a.steps / el2, "affine_cells_per_gpu": sol2.naff, "cells_per_gpu": sol2.ncells,
                   "algorithmic_bytes_per_stage": sol2.stage_bytes(),
                   "note": "solver(geometry='auto'): G = wq x Gc on cells with a constant Jacobian (all cells of "
@@ -713,9 +722,11 @@ def main():
         "stage_roofline": {"bound": "hbm", "achieved": stage_bytes / stage_t / 1e9, "peak": peak, "unit": "GB/s",
                            "frac": stage_bytes / stage_t / 1e9 / peak,
                            "algorithmic_bytes_per_stage": stage_bytes, "stage_ms": stage_t * 1e3,
-                           "bytes_model": "stage kernel bytes + 10.25 vector passes per stage (what the fused "
-                                          "ping-pong stages move: 9 + 12 + 12 + 8 per step)",
-                           "survey_8d_model": {"algorithmic_bytes_per_stage": solver.stage_bytes_survey(),
+                           "bytes_model": ("stage kernel bytes + 10.25 vector passes per stage (what the fused "
+                                           "ping-pong stages move: 9 + 12 + 12 + 8 per step)" if NST == 4 else
+                                           "stiffness bytes + 7 vector passes per leapfrog step"),
+                           "survey_8d_model": None if NST != 4 else {
+                                               "algorithmic_bytes_per_stage": solver.stage_bytes_survey(),
                                                "frac": solver.stage_bytes_survey() / stage_t / 1e9 / peak,
                                                "note": "SURVEY.md 8(d): 6s + stiffness + 8s per dof, more than "
                                                        "this implementation moves"}},

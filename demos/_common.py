@@ -33,6 +33,8 @@ def parser(desc, degree, cells):
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--geometry", default="stream", choices=["stream", "auto"],
                     help="auto: affine cells keep 6 geometric factors instead of 6 n^3 (same results to rounding)")
+    ap.add_argument("--integrator", default="rk4", choices=["rk4", "leapfrog"],
+                    help="time integrator of the linear demos: rk4 (the reference's) or leapfrog")
     ap.add_argument("--sample-dir", default=None,
                     help="write pressure_field_<k>.txt dumps of the sampling plane here (device-side sampling)")
     return ap

@@ -20,7 +20,7 @@ def main():
     lengths = tuple(h * n for n in ncells)
     su = problem.box_setup(a.degree, ncells, lengths, dtype, rank, world, grid=grid)
     solver = problem.linear_solver(su, source_facets=[2], absorbing_facets=[3], rho=rho, c0=c0, f0=f0, p0=p0,
-                                   geometry=a.geometry)
+                                   geometry=a.geometry, integrator=a.integrator)
     dt = problem.cfl_time_step(a.degree, h, c0, f0, 0.65)  # :116-120
     tf = lengths[0] / c0 + 2.0 / f0  # :121
     nsteps = a.steps or int(tf / dt) + 1

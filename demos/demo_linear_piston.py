@@ -26,7 +26,7 @@ def main():
     solver = problem.linear_solver(
         su, source_facets=[0], absorbing_facets=[0, 1, 2, 3, 4, 5], rho=rho, c0=c0, f0=f0, p0=p0,
         source_predicate=piston, absorbing_predicate=lambda cen: ~(piston(cen) & (cen[:, 2] < 0.5 * h)),
-        geometry=a.geometry)
+        geometry=a.geometry, integrator=a.integrator)
     dt = problem.cfl_time_step(a.degree, h, c0, f0, 0.65)
     tf = lengths[2] / c0 + 8.0 / f0  # :110
     nsteps = a.steps or int(tf / dt) + 1

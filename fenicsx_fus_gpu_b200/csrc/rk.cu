@@ -149,10 +149,29 @@ struct CloseArgs {
 // cell-mass pair of cuda/demo_nonlinear_bowl.py:609-612, 626-628 is pointwise:
 //   M(c2; un) = un * M(c2; 1) = un * m2,   M(c5; vn^2) = vn^2 * m5
 // and kv = (b + vn^2 m5) / (m0 + un m2) with un, vn the stage input (un still holds it here).
+// WEST 3: not an RK stage but a whole LEAPFROG step of the second-order system (u at whole steps,
+// v at half steps; the reference implements RK4 only, the north star also names leapfrog):
+//   v += bdt * b / m ; u += adt_next * v ; b = 0
+// with m = m_lumped - (dt/2) absb, which makes the absorbing term a (v+ + v-)/2 time-centred
+// (second order, unconditionally damping) at no extra cost.  4 reads + 3 writes per dof.
 template <typename T, bool VEC, int WEST>
 __device__ __forceinline__ void close_body(const CloseArgs<T>& a, long long k) {
   constexpr int W = VEC ? Vec<T>::W : 1;
   using P = Pack<T, Vec<T>::W>;
+  if constexpr (WEST == 3) {
+    const P b = ld<T, VEC>(a.b, k), m = ld<T, VEC>(a.m, k);
+    P u = ld<T, VEC>(a.u, k), v = ld<T, VEC>(a.v, k), z;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      v.v[w] = a.bdt * (b.v[w] / m.v[w]) + v.v[w];
+      u.v[w] = a.adt_next * v.v[w] + u.v[w];
+      z.v[w] = T(0);
+    }
+    st<T, VEC>(a.u, k, u);
+    st<T, VEC>(a.v, k, v);
+    st<T, VEC>(a.b, k, z);
+    return;
+  }
   P b = ld<T, VEC>(a.b, k);
   P m;
   if constexpr (WEST == 2) {
@@ -396,6 +415,8 @@ int close_entry(T* u, T* v, T* u0, T* v0, T* ku, T* kv, T* un, T* b, T* m, const
   if (n == 0) return 0;
   if (WEST == 2 && (m0 == nullptr || m2 == nullptr || m5 == nullptr))
     return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close_westervelt_pw: null m0 / m2 / m5");
+  if (WEST == 3 && (u == nullptr || v == nullptr || b == nullptr || m == nullptr))
+    return fus_set_error(FUS_ERR_BAD_ARGUMENT, "leapfrog_close: null vector");
   CloseArgs<T> a{u, v, u0, v0, ku, kv, un, b, m, m0, m2, m5, bdt, adt_next, next_mode, n,
                  reinterpret_cast<long long*>(step), skip};
   cudaStream_t st_ = static_cast<cudaStream_t>(stream);
@@ -414,11 +435,13 @@ int close_shared_entry(fus_halo* halo, int variant, int put_next, int gather, T*
                        T* m, const T* m0, const T* m2, const T* m5, T bdt, T adt_next, int next_mode,
                        void* stream) {
   if (halo == nullptr) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close_shared: null halo handle");
-  if (variant < 0 || variant > 2) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close_shared: variant");
+  if (variant < 0 || variant > 3) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close_shared: variant");
   if (next_mode < 1 || next_mode > 4) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close_shared: next_mode 1..4");
   if ((variant >= 1 && m0 == nullptr) || (variant == 2 && (m2 == nullptr || m5 == nullptr)) ||
-      (variant <= 1 && m == nullptr))
+      ((variant <= 1 || variant == 3) && m == nullptr))
     return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close_shared: null mass vector");
+  if (variant == 3 && next_mode != 4)
+    return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close_shared: the leapfrog variant takes next_mode 4");
   const FusHaloDev& h = *fus_halo_dev_of(halo);
   if (h.nu == 0) return 0;  // nothing shared: nobody ghosts my dofs, nobody waits for my signal
   CloseArgs<T> a{u, v, u0, v0, ku, nullptr, un, b, m, m0, m2, m5, bdt, adt_next, next_mode, h.size_local,
@@ -432,6 +455,8 @@ int close_shared_entry(fus_halo* halo, int variant, int put_next, int gather, T*
     rk_close_shared_kernel<T, 0><<<(unsigned)blocks, kSharedThreads, 0, st_>>>(a, h, put, gat);
   } else if (variant == 1) {
     rk_close_shared_kernel<T, 1><<<(unsigned)blocks, kSharedThreads, 0, st_>>>(a, h, put, gat);
+  } else if (variant == 3) {
+    rk_close_shared_kernel<T, 3><<<(unsigned)blocks, kSharedThreads, 0, st_>>>(a, h, put, gat);
   } else {
     rk_close_shared_kernel<T, 2><<<(unsigned)blocks, kSharedThreads, 0, st_>>>(a, h, put, gat);
   }
@@ -493,6 +518,12 @@ extern "C" {
                                        const uint8_t* skip_mask, void* s) {                      \
     return close_entry<T, 2>(u, v, u0, v0, ku, kv, un, b, nullptr, m0, bdt, adt_next, next_mode, \
                              n, step_dev, skip_mask, s, m2, m5);                                 \
+  }                                                                                              \
+  int fus_leapfrog_close_##SFX(T* u, T* v, T* b, const T* m, T dt_v, T dt_u, int64_t n,          \
+                               int64_t* step_dev, const uint8_t* skip_mask, void* s) {           \
+    return close_entry<T, 3>(u, v, nullptr, nullptr, nullptr, nullptr, nullptr, b,               \
+                             const_cast<T*>(m), nullptr, dt_v, dt_u, 4, n, step_dev, skip_mask,  \
+                             s);                                                                 \
   }                                                                                              \
   int fus_boundary_terms_##SFX(T* b, const T* vn, const int32_t* dof, const T* src,              \
                                const T* src2, const T* absb, T g, T dg, const T* gtab,           \

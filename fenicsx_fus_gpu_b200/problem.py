@@ -26,7 +26,7 @@ from . import precompute as pre
 from . import substrate as S
 from . import utils
 from .scatterer import HaloExchange, P2PHaloExchange, SymmFabric
-from .solver import LinearSpectral3D, WesterveltSpectral3D, linear_source, westervelt_source
+from .solver import LinearLeapfrog3D, LinearSpectral3D, WesterveltSpectral3D, linear_source, westervelt_source
 
 
 @dataclass
@@ -148,14 +148,19 @@ def cfl_time_step(P, h, c0, f0, cfl):
 
 
 def linear_solver(su: Setup, source_facets, absorbing_facets, rho=1000.0, c0=1500.0, f0=0.5e6,
-                  p0=60000.0, source_predicate=None, absorbing_predicate=None, **kw) -> LinearSpectral3D:
-    """cuda/demo_linear_box.py:336-345 coefficients + the fused solver."""
+                  p0=60000.0, source_predicate=None, absorbing_predicate=None, integrator="rk4",
+                  **kw) -> LinearSpectral3D:
+    """cuda/demo_linear_box.py:336-345 coefficients + the fused solver (``integrator``: "rk4", the
+    reference's scheme, or "leapfrog")."""
+    if integrator not in ("rk4", "leapfrog"):
+        raise ValueError("integrator must be 'rk4' or 'leapfrog'")
+    cls = LinearLeapfrog3D if integrator == "leapfrog" else LinearSpectral3D
     nc = su.mesh.num_cells
     if kw.get("geometry") == "auto":
         kw.setdefault("weights", su.tables.wts)
     fd1, dJ1, bd1 = facet_group(su, source_facets, source_predicate)
     fd2, dJ2, bd2 = facet_group(su, absorbing_facets, absorbing_predicate)
-    return LinearSpectral3D(
+    return cls(
         su.P, su.dtype, su.ndofs, su.dev["dofmap"], su.dev["G"], su.dev["detJ"], su.tables.dphi_1D,
         _full(su, nc, 1.0 / rho / c0 / c0), _full(su, nc, -1.0 / rho),
         fd1, dJ1, _full(su, bd1.shape[0], 1.0 / rho), fd2, dJ2, _full(su, bd2.shape[0], -1.0 / rho / c0),

@@ -42,7 +42,7 @@ def _solver(su, workload, **kw):
 
 
 def multi_gpu_parity(P=4, n_per_rank=6, dtype=np.float64, nsteps=8, workload="linear", halo_kind="p2p",
-                     use_graph=True, geometry="stream", perturb=0.1, split_cells=True, split_mode="none", group=None):
+                     use_graph=True, geometry="stream", perturb=0.1, split_cells=True, split_mode="none", integrator="rk4", group=None):
     """rel-L2 of the partitioned solve against the single-GPU solve of the same global box.
 
     Collective over ``group`` (default: world).  Returns a dict on every rank
@@ -59,6 +59,9 @@ def multi_gpu_parity(P=4, n_per_rank=6, dtype=np.float64, nsteps=8, workload="li
     c0, f0, cfl = (1500.0, 0.5e6, 0.65) if workload in ("linear", "piston") else (1480.0, 1.1e6, 0.4)
     dt = problem.cfl_time_step(P, h * (1.0 - 2.0 * perturb), c0, f0, cfl)
     kw = dict(geometry=geometry, use_graph=use_graph)
+    if integrator != "rk4":
+        kw["integrator"] = integrator  # linear workloads only
+        dt = 0.5 * dt
 
     su = problem.box_setup(P, ncells, lengths, dtype, rank, world, comm=group, grid=grid, perturb=perturb, seed=7,
                            halo_kind=halo_kind)
@@ -74,7 +77,7 @@ def multi_gpu_parity(P=4, n_per_rank=6, dtype=np.float64, nsteps=8, workload="li
     parts = [None] * world
     dist.all_gather_object(parts, mine, group=group)
     out = dict(workload=workload, degree=P, dtype=dtype.name, n_gpus=world, global_cells=list(ncells),
-               global_dofs=int(su.global_dofs), steps=nsteps, halo=halo_kind, geometry=geometry, split_mode=split_mode,
+               global_dofs=int(su.global_dofs), steps=nsteps, halo=halo_kind, geometry=geometry, split_mode=split_mode, integrator=integrator,
                graph=bool(use_graph and sol._graph is not None), interface_cells=int(sol.ninterface),
                shared_dofs=int(getattr(sol.halo, "nshared", 0)), tol=TOL[dtype])
     res = [0.0, 0.0, 0.0]

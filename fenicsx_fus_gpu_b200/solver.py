@@ -663,6 +663,7 @@ class LinearSpectral3D(_RK4):
         if bd2.shape[0]:
             terms.append(("absb", bd2, _dev(detJ_f2, self.T), _dev(facet_coeff2, self.T)))
         self._boundary_setup(terms)
+        self._abs_facets = (bd2, _dev(detJ_f2, self.T), _dev(facet_coeff2, self.T)) if bd2.shape[0] else None
         self._setup_geometry(None, ["cell_coeff2"])
 
     def _stiffness(self, x=None, wait=False):
@@ -701,6 +702,126 @@ class LinearSpectral3D(_RK4):
             self.halo.handle, 0, 1, 1, u, v, u0, v0, self.ku.data_ptr(), self.un.data_ptr(),
             self.b.data_ptr(), self.m.data_ptr(), None, None, None, bdt, adt, mode, current_stream()),
             "fus_rk_close_shared")
+
+
+class LinearLeapfrog3D(LinearSpectral3D):
+    """The same linear wave problem advanced with the LEAPFROG (Stoermer-Verlet) scheme instead of
+    RK4: ``u`` lives at whole steps, ``v`` at half steps,
+
+        b = K(-1/rho; u^n) + g(t_n) src + absb v^{n-1/2}
+        v^{n+1/2} = v^{n-1/2} + dt b / (m - dt/2 absb)        (absorbing term time-centred)
+        u^{n+1}   = u^n + dt v^{n+1/2}
+
+    ONE stiffness action and 7 vector passes per step (RK4: four and 41), second order in time,
+    stable for ``dt <= 2 / sqrt(lambda_max)`` (RK4: 2.78 / sqrt(lambda_max)).  The north star names
+    "RK4/leapfrog"; the reference implements RK4 only (cuda/demo_linear_box.py:437-567), so this
+    scheme has no reference twin: it is pinned to the oracle's restatement (bit-for-bit the same
+    operations) and to its convergence order against the RK4 solution (tests/test_gpu_leapfrog.py).
+
+    Same constructor as ``LinearSpectral3D``; ``rk4`` is kept as the stepping entry point (alias
+    ``steps``) so the demos, ``bench.py`` and the graph machinery drive either integrator.
+    After ``n`` steps ``u`` is ``u(t_n)`` and ``v`` is ``v(t_n - dt/2)``."""
+
+    integrator = "leapfrog"
+
+    def __init__(self, *args, **kw):
+        super().__init__(*args, **kw)
+        torch = _torch()
+        # owner-complete diagonal of the absorbing facet term (the compact list of _boundary_setup
+        # holds this rank's partial sums, which is what the assembly needs)
+        self._absd = torch.zeros(self.ndofs, dtype=self.T, device="cuda") if not self.p2p else self._zx()
+        if self._abs_facets is not None:
+            bd2, dJ2, fc2 = self._abs_facets
+            ones = torch.ones(self.ndofs, dtype=self.T, device="cuda")
+            self._mass(ones, fc2, self._absd, dJ2, bd2)
+        if self.halo is not None:
+            self.halo.reverse(self._absd)
+        self._mlf = None
+        self._mlf_dt = None
+
+    @property
+    def u(self):
+        return self._uv[0][0]
+
+    @property
+    def v(self):
+        return self._uv[0][1]
+
+    def begin_steps(self):
+        if self.p2p:
+            self.halo.barrier()
+            self.halo.put(*self._uv[0])
+
+    def _lf_close(self, m, dt_v, dt_u, count_step, skip=None):
+        u, v = self._uv[0]
+        check(fn("fus_leapfrog_close", self.dtype)(
+            u.data_ptr(), v.data_ptr(), self.b.data_ptr(), m.data_ptr(), dt_v, dt_u, self.nupd,
+            self.step_dev.data_ptr() if count_step else None, skip, current_stream()), "fus_leapfrog_close")
+
+    def _kick(self, t0, dt):
+        """v(t0) -> v(t0 - dt/2): half a step backwards with the acceleration at t0."""
+        u, v = self._uv[0]
+        g = self.source(t0)[0] if self.source is not None else 0.0
+        if self.halo is not None:
+            self.halo.forward(u, v)
+        self._assemble(0, g, 0.0, False, u, v)
+        self._boundary(0, g, 0.0, False, v)
+        if self.halo is not None:
+            self.halo.reverse(self.b)
+        self._lf_close(self.m, -0.5 * dt, 0.0, False)
+        if self.p2p and self.ndofs > self.nupd:
+            self.b[self.nupd:].zero_()  # the stand-alone reverse keeps the ghost sums; the steps expect them cleared
+
+    def rk4(self, t0, dt, nsteps):
+        """``nsteps`` leapfrog steps of size ``dt`` from ``t0`` (the name is the solvers' common
+        stepping entry point); returns the final time."""
+        if self._mlf_dt != dt:
+            self._mlf = (self.m - (0.5 * dt) * self._absd).contiguous()
+            self._mlf_dt = dt
+        if not self._opened:
+            self._set_tables()
+            self._open_first()
+            self._kick(float(t0), dt)
+        return super().rk4(t0, dt, nsteps)
+
+    steps = rk4
+
+    def step_eager(self, dt):
+        raise NotImplementedError("LinearLeapfrog3D: use rk4 / steps")
+
+    def _enqueue_step(self, dt, t, use_table, parity=None):
+        u, v = self._uv[0]
+        g = 0.0
+        if not use_table and self.source is not None:
+            g = self.source(t)[0]
+        h = self.halo
+        if self.p2p:
+            h.wait_forward()
+            self._assemble(0, g, 0.0, use_table, u, v)
+            self._boundary(0, g, 0.0, use_table, v, signal=True)
+            h.fork()
+            with h.side():
+                h.wait_reverse()
+                check(fn("fus_rk_close_shared", self.dtype)(
+                    h.handle, 3, 1, 1, u.data_ptr(), v.data_ptr(), None, None, None, None, self.b.data_ptr(),
+                    self._mlf.data_ptr(), None, None, None, dt, dt, 4, current_stream()), "fus_rk_close_shared")
+            self._lf_close(self._mlf, dt, dt, use_table, skip=h.shared_mask)
+            h.join()
+            return
+        if h is not None:
+            h.forward(u, v)
+        self._assemble(0, g, 0.0, use_table, u, v)
+        self._boundary(0, g, 0.0, use_table, v)
+        if h is not None:
+            h.reverse(self.b)
+        self._lf_close(self._mlf, dt, dt, use_table)
+
+    def stage_bytes(self):
+        """Algorithmic HBM bytes of one leapfrog STEP: one stiffness action + 7 vector passes."""
+        s = self.dtype.itemsize
+        Nd = self.n**3
+        nstream = self.ncells - self.naff
+        return nstream * (Nd * 4 + 6 * Nd * s + s) + self.naff * (Nd * 4 + 7 * s) + 2 * s * self.ndofs + 7 * s * self.ndofs
 
 
 class WesterveltSpectral3D(_RK4):

@@ -380,7 +380,8 @@ int fus_rk_close_f32(float* u, float* v, float* u0, float* v0, float* ku, float*
  * (call fus_halo_wait_reverse first): each thread adds the neighbours' ghost partial sums of its
  * dof to b (and m, variant 1), loaded straight from their vectors, and clears them there - no
  * get_add pass, no atomics, no kernel to zero the ghost accumulators.  variant 0: fus_rk_close (m); 1: fus_rk_close_westervelt
- * (m, m0); 2: fus_rk_close_westervelt_pw (m0, m2, m5); unused mass pointers may be NULL.
+ * (m, m0); 2: fus_rk_close_westervelt_pw (m0, m2, m5); 3: fus_leapfrog_close (m; next_mode 4, bdt =
+ * dt_v, adt_next = dt_u); unused mass pointers may be NULL.
  * Replaces scatter_reverse(b) -> pointwise_divide/axpy -> (next stage) scatter_forward(un),
  * scatter_forward(vn) of cuda/demo_linear_box.py:536-563. */
 int fus_rk_close_shared_f64(fus_halo_t* halo, int variant, int put_next, int gather, double* u,
@@ -391,6 +392,19 @@ int fus_rk_close_shared_f32(fus_halo_t* halo, int variant, int put_next, int gat
                             float* v, float* u0, float* v0, float* ku, float* un, float* b, float* m,
                             const float* m0, const float* m2, const float* m5, float bdt,
                             float adt_next, int next_mode, void* stream);
+
+/* One LEAPFROG step of the same second-order system (the north star names "RK4/leapfrog"; the
+ * reference implements RK4 only - cuda/demo_linear_box.py:487-567 - so this has no reference
+ * twin and is pinned to the oracle's restatement of the scheme and to its convergence order):
+ *   v += dt_v * b / m ; u += dt_u * v ; b = 0        (u at whole steps, v at half steps)
+ * b = K u + g src + absb v as assembled by fus_stiffness_* + fus_boundary_terms_*; with
+ * m = m_lumped - (dt/2) absb the absorbing term is time-centred.  One stiffness action per step
+ * instead of RK4's four; 4 reads + 3 writes per dof.  step_dev / skip_mask as for fus_rk_close_*;
+ * the multi-GPU twin is fus_rk_close_shared_* with variant 3 (next_mode 4: u, v are put). */
+int fus_leapfrog_close_f64(double* u, double* v, double* b, const double* m, double dt_v, double dt_u,
+                           int64_t n, int64_t* step_dev, const uint8_t* skip_mask, void* stream);
+int fus_leapfrog_close_f32(float* u, float* v, float* b, const float* m, float dt_v, float dt_u,
+                           int64_t n, int64_t* step_dev, const uint8_t* skip_mask, void* stream);
 
 /* Boundary-facet terms of one stage through precomputed diagonals on a compact
  * list of UNIQUE dofs: b[dof[i]] += g * src[i] + dg * src2[i] + vn[dof[i]] * absb[i].

@@ -416,6 +416,43 @@ def linear_rk4(prob: LinearProblem, u_, v_, t, dt, nsteps, scatter_fwd=None, sca
     return t
 
 
+def linear_leapfrog(prob: LinearProblem, u_, v_, t, dt, nsteps, absd=None):
+    """Leapfrog (Stoermer-Verlet) restatement for the product's ``LinearLeapfrog3D`` - NOT in
+    the reference (which implements RK4 only); same assembly as ``linear_rk4``'s f(), operation
+    for operation what the CUDA step does:
+        kick-off  : v <- v - dt/2 * b(t, u, v) / m
+        each step : b = K u + g(t) src + absb v ; v += dt * b / (m - dt/2 absd) ; u += dt * v
+    ``absd`` = the absorbing facet mass applied to ones (default: computed here).  On return
+    ``u_`` is u(t + nsteps dt) and ``v_`` is v at the last half step."""
+    dt_type = u_.dtype.type
+    nd = u_.size
+    b = np.zeros(nd, u_.dtype)
+    g = np.zeros(nd, u_.dtype)
+    if absd is None:
+        absd = np.zeros(nd, u_.dtype)
+        if prob.bfacet_dofmap2.shape[0]:
+            mass_operator(np.ones(nd, u_.dtype), prob.facet_coeff2, absd, prob.detJ_f2, prob.bfacet_dofmap2)
+
+    def assemble(tt):
+        fill(dt_type(linear_source(tt, prob.f0, prob.p0, prob.c0)), g)
+        fill(dt_type(0.0), b)
+        stiffness_operator(prob.P, u_, prob.cell_coeff2, b, prob.G, prob.dofmap, prob.dphi_1D)
+        if prob.bfacet_dofmap1.shape[0]:
+            mass_operator(g, prob.facet_coeff1, b, prob.detJ_f1, prob.bfacet_dofmap1)
+        if prob.bfacet_dofmap2.shape[0]:
+            mass_operator(v_, prob.facet_coeff2, b, prob.detJ_f2, prob.bfacet_dofmap2)
+
+    assemble(t)
+    v_ += dt_type(-0.5 * dt) * (b / prob.m)
+    mlf = prob.m - dt_type(0.5 * dt) * absd
+    for _ in range(nsteps):
+        assemble(t)
+        v_ += dt_type(dt) * (b / mlf)
+        u_ += dt_type(dt) * v_
+        t += dt
+    return t
+
+
 def westervelt_source(t, f0, p0, c0, alpha=4.0):
     """cuda/demo_nonlinear_bowl.py:560-594: g and dg/dt."""
     T = 1.0 / f0

@@ -92,6 +92,7 @@ def main():
         dict(workload="linear", P=4, n_per_rank=6, dtype="float64", nsteps=8, split_mode="fused"),
         dict(workload="linear", P=4, n_per_rank=6, dtype="float64", nsteps=8, halo_kind="nccl"),
         dict(workload="westervelt", P=4, n_per_rank=5, dtype="float64", nsteps=6),
+        dict(workload="linear", P=4, n_per_rank=6, dtype="float64", nsteps=12, integrator="leapfrog"),
     ]
     if not a.quick:
         cases += [
@@ -114,7 +115,7 @@ def main():
         results.append(r)
         if rank == 0:
             print(f"[mgpu] {r['workload']} P{r['degree']} {r['dtype']} halo={r['halo']} geometry={r['geometry']} "
-                  f"graph={r['graph']} split={r['split_mode']} iface={r['interface_cells']}: rel-L2 u {r['rel_l2_u']:.2e} v {r['rel_l2_v']:.2e} "
+                  f"{r['integrator']} graph={r['graph']} split={r['split_mode']} iface={r['interface_cells']}: rel-L2 u {r['rel_l2_u']:.2e} v {r['rel_l2_v']:.2e} "
                   f"{'ok' if r['ok'] else 'FAIL'}", flush=True)
     sc = scatter_cases(rank, world)
     allsc = [None] * world

@@ -15,6 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 DEMOS = [
     ("demo_linear_box.py", ["--cells", "6", "--steps", "2"]),
+    ("demo_linear_box.py", ["--cells", "6", "--steps", "2", "--integrator", "leapfrog"]),
     ("demo_linear_piston.py", ["--cells", "5", "--steps", "2"]),
     ("demo_nonlinear_bowl.py", ["--cells", "5", "--steps", "2"]),
     ("demo_nonlinear_box.py", ["--cells", "4", "--steps", "2"]),
