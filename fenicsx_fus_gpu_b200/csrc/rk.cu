@@ -437,7 +437,7 @@ int close_shared_entry(fus_halo* halo, int variant, int put_next, int gather, T*
   if (halo == nullptr) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close_shared: null halo handle");
   if (variant < 0 || variant > 3) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close_shared: variant");
   if (next_mode < 1 || next_mode > 4) return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close_shared: next_mode 1..4");
-  if ((variant >= 1 && m0 == nullptr) || (variant == 2 && (m2 == nullptr || m5 == nullptr)) ||
+  if (((variant == 1 || variant == 2) && m0 == nullptr) || (variant == 2 && (m2 == nullptr || m5 == nullptr)) ||
       ((variant <= 1 || variant == 3) && m == nullptr))
     return fus_set_error(FUS_ERR_BAD_ARGUMENT, "rk_close_shared: null mass vector");
   if (variant == 3 && next_mode != 4)
