@@ -420,20 +420,28 @@ def main():
     if world > 1:
         from fenicsx_fus_gpu_b200.selfcheck import multi_gpu_parity
 
-        log("multi-GPU parity leg")
-        pr = multi_gpu_parity(P=deg, n_per_rank=max(4, 24 // deg), dtype=dtype, nsteps=8,
-                              workload="westervelt" if W["nonlinear"] else "linear", halo_kind=a.halo,
-                              use_graph=not a.no_graph, split_cells=not a.no_split)
-        parity = {k: pr[k] for k in ("rel_l2_u", "rel_l2_v", "tol", "ok", "global_cells", "global_dofs", "steps", "halo",
-                                     "graph", "interface_cells", "shared_dofs")}
-        parity["what"] = ("one global box solved on all ranks (this run's halo, graph replay) vs the same box on "
-                          "rank 0 alone: rel-L2 of the gathered state")
-        if not pr["ok"]:
-            if rank == 0:
-                os.dup2(stdout_fd, 1)
-                print(json.dumps({"metric": METRIC, "value": None, "n_gpus": world, "multi_gpu_parity": parity,
-                                  "error": "multi-GPU parity check failed: not timing a wrong answer"}), flush=True)
-            os._exit(3)
+        keys = ("rel_l2_u", "rel_l2_v", "tol", "ok", "global_cells", "global_dofs", "steps", "halo", "graph",
+                "interface_cells", "shared_dofs", "partition")
+        for part_kind in ("block", "blob"):
+            log(f"multi-GPU parity leg ({part_kind} partition)")
+            pr = multi_gpu_parity(P=deg, n_per_rank=max(4, 24 // deg), dtype=dtype, nsteps=8,
+                                  workload="westervelt" if W["nonlinear"] else "linear", halo_kind=a.halo,
+                                  use_graph=not a.no_graph, split_cells=not a.no_split, partition=part_kind)
+            leg = {k: pr[k] for k in keys}
+            if part_kind == "block":
+                parity = leg
+                parity["what"] = ("one global box solved on all ranks (this run's halo, graph replay) vs the same box "
+                                  "on rank 0 alone: rel-L2 of the gathered state")
+            else:
+                leg["what"] = ("the same check on an unstructured-like partition: irregular connected parts, shuffled "
+                               "cell / dof / ghost order, pseudo-random ownership of the shared dofs")
+                parity["unstructured_like"] = leg
+            if not pr["ok"]:
+                if rank == 0:
+                    os.dup2(stdout_fd, 1)
+                    print(json.dumps({"metric": METRIC, "value": None, "n_gpus": world, "multi_gpu_parity": parity,
+                                      "error": "multi-GPU parity check failed: not timing a wrong answer"}), flush=True)
+                os._exit(3)
 
     log("building the problem")
     solver, info = build_problem(rank, world, n_per_gpu, dtype, a.halo, a.workload, deg, a.geometry,

@@ -58,11 +58,15 @@ def _d(a):
 
 def box_setup(P, ncells, lengths, dtype=np.float64, rank=0, world=1, comm=None, grid=None,
               perturb=0.0, seed=0, order="basix", max_halo_vecs=3, scatter_data=None,
-              halo_kind="nccl", fabric=None) -> Setup:
+              halo_kind="nccl", fabric=None, partition="block") -> Setup:
     """Mesh part, dofmap, halo and device geometry of rank ``rank`` of ``world``.
 
     ``comm``: torch.distributed group / transport for the halo (None = world
-    group when ``world > 1``)."""
+    group when ``world > 1``).  ``partition``: ``"block"`` (``substrate.partition_box``, the
+    rank grid) or ``"blob"`` - an unstructured-like partition (``substrate.partition_cells``:
+    irregular connected parts, shuffled cell / dof / ghost order, pseudo-random ownership of
+    the shared dofs), which exercises the generic index-map -> halo path the way a graph
+    partitioner's output would."""
     import torch
 
     dtype = np.dtype(dtype)
@@ -79,8 +83,15 @@ def box_setup(P, ncells, lengths, dtype=np.float64, rank=0, world=1, comm=None, 
         dofmap = S.tensor_dofmap(mesh, P, order)
         ndofs = nlocal = S.num_dofs(ncells, P)
     else:
-        part = S.partition_box(ncells, P, world, lengths=lengths, order=order, dtype=dtype,
-                               perturb=perturb, seed=seed, ranks=[rank], grid=grid)[0]
+        if partition == "blob":
+            part = S.partition_cells(ncells, P, S.blob_cell_ranks(ncells, world, seed=seed), lengths=lengths,
+                                     order=order, dtype=dtype, perturb=perturb, seed=seed, shuffle_seed=seed + 1,
+                                     owner_rule="hash")[rank]
+        elif partition == "block":
+            part = S.partition_box(ncells, P, world, lengths=lengths, order=order, dtype=dtype,
+                                   perturb=perturb, seed=seed, ranks=[rank], grid=grid)[0]
+        else:
+            raise ValueError("partition must be 'block' or 'blob'")
         mesh, dofmap = part.mesh, part.dofmap
         l2s = part.local_to_serial
         nlocal = part.index_map.size_local

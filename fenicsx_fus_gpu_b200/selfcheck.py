@@ -42,8 +42,11 @@ def _solver(su, workload, **kw):
 
 
 def multi_gpu_parity(P=4, n_per_rank=6, dtype=np.float64, nsteps=8, workload="linear", halo_kind="p2p",
-                     use_graph=True, geometry="stream", perturb=0.1, split_cells=True, split_mode="none", integrator="rk4", group=None):
+                     use_graph=True, geometry="stream", perturb=0.1, split_cells=True, split_mode="none", integrator="rk4", group=None,
+                     partition="block"):
     """rel-L2 of the partitioned solve against the single-GPU solve of the same global box.
+    ``partition="blob"``: irregular parts with shuffled numbering (``problem.box_setup``) instead
+    of the rank grid.
 
     Collective over ``group`` (default: world).  Returns a dict on every rank
     (``rel_l2_u``, ``rel_l2_v``, ``ok``, ...)."""
@@ -64,7 +67,7 @@ def multi_gpu_parity(P=4, n_per_rank=6, dtype=np.float64, nsteps=8, workload="li
         dt = 0.5 * dt
 
     su = problem.box_setup(P, ncells, lengths, dtype, rank, world, comm=group, grid=grid, perturb=perturb, seed=7,
-                           halo_kind=halo_kind)
+                           halo_kind=halo_kind, partition=partition)
     sol = _solver(su, workload, split_cells=split_cells, **kw)
     sol.split_mode = split_mode
     sol.init()
@@ -77,7 +80,7 @@ def multi_gpu_parity(P=4, n_per_rank=6, dtype=np.float64, nsteps=8, workload="li
     parts = [None] * world
     dist.all_gather_object(parts, mine, group=group)
     out = dict(workload=workload, degree=P, dtype=dtype.name, n_gpus=world, global_cells=list(ncells),
-               global_dofs=int(su.global_dofs), steps=nsteps, halo=halo_kind, geometry=geometry, split_mode=split_mode, integrator=integrator,
+               global_dofs=int(su.global_dofs), steps=nsteps, halo=halo_kind, geometry=geometry, partition=partition, split_mode=split_mode, integrator=integrator,
                graph=bool(use_graph and sol._graph is not None), interface_cells=int(sol.ninterface),
                shared_dofs=int(getattr(sol.halo, "nshared", 0)), tol=TOL[dtype])
     res = [0.0, 0.0, 0.0]

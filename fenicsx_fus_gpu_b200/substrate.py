@@ -257,6 +257,9 @@ class BoxMesh:
     cell_origin: tuple = (0, 0, 0)  # offset of this part in the global cell grid
     global_ncells: tuple = None
     lengths: tuple = (1.0, 1.0, 1.0)
+    # parts that are not boxes (partition_cells): global lexicographic id of every local cell;
+    # ``ncells`` / ``cell_origin`` then carry no meaning
+    cell_ids: np.ndarray = None
 
     @property
     def num_cells(self) -> int:
@@ -387,6 +390,17 @@ def boundary_facets(mesh: BoxMesh, local_facet: int, predicate=None) -> np.ndarr
     ``predicate(centroids (nf,3)) -> bool mask`` optionally filters them.
     """
     axis, side = _FACE_AXIS[local_facet]
+    if mesh.cell_ids is not None:  # arbitrary set of cells of the global box, arbitrary order
+        gN = mesh.global_ncells
+        ids = np.asarray(mesh.cell_ids, dtype=np.int64)
+        pos = (ids // (gN[1] * gN[2]), (ids // gN[2]) % gN[1], ids % gN[2])[axis]
+        cells = np.nonzero(pos == (0 if side == 0 else gN[axis] - 1))[0]
+        out = np.stack([cells, np.full_like(cells, local_facet)], axis=1).astype(np.int32)
+        if predicate is not None and cells.size:
+            fv = [v for v in range(8) if ((v >> axis) & 1) == side]
+            cen = mesh.x_g[mesh.x_dofs[cells][:, fv]].mean(axis=1)
+            out = out[np.asarray(predicate(cen), dtype=bool)]
+        return np.ascontiguousarray(out.reshape(-1, 2))
     N = mesh.ncells
     org = mesh.cell_origin
     gN = mesh.global_ncells or N
@@ -623,6 +637,121 @@ def partition_box(
             ghosts, ghost_owners, AdjacencyList(d_arr, d_off),
         )
         parts.append(Partition(rank, nranks, mesh, dofmap, imap, l2g, l2s))
+    return parts
+
+
+def blob_cell_ranks(ncells, nranks: int, seed: int = 0) -> np.ndarray:
+    """An irregular cell -> rank assignment for ``partition_cells``: every cell goes to the nearest
+    of ``nranks`` random seed points (in a randomly stretched metric), so the parts are connected
+    blobs with staircase interfaces, different sizes and different numbers of neighbours - the shape
+    of a graph partitioner's output, not a block grid.  Every rank gets at least one cell."""
+    if np.isscalar(ncells):
+        ncells = (int(ncells),) * 3
+    rng = np.random.default_rng(seed)
+    cx, cy, cz = np.meshgrid(*[np.arange(n) + 0.5 for n in ncells], indexing="ij")
+    cen = np.stack([cx.ravel(), cy.ravel(), cz.ravel()], axis=1)
+    for _ in range(100):
+        pts = rng.uniform(0, 1, (nranks, 3)) * np.array(ncells)
+        w = rng.uniform(0.6, 1.6, (nranks, 3))
+        d2 = (((cen[:, None, :] - pts[None, :, :]) * w[None, :, :]) ** 2).sum(axis=2)
+        ranks = np.argmin(d2, axis=1).astype(np.int32)
+        if np.unique(ranks).size == nranks:
+            return ranks
+    raise RuntimeError("blob_cell_ranks: could not give every rank a cell")
+
+
+def partition_cells(
+    ncells,
+    P: int,
+    cell_rank: np.ndarray,
+    lengths=(1.0, 1.0, 1.0),
+    order: str = "basix",
+    dtype=np.float64,
+    perturb: float = 0.0,
+    seed: int = 0,
+    shuffle_seed=None,
+    owner_rule: str = "lowest",
+):
+    """Partition a box mesh by an ARBITRARY cell -> rank map (``cell_rank[c]`` for the global
+    lexicographic cell ``c``), the way a graph partitioner hands an unstructured mesh to DOLFINx
+    with ``GhostMode.none``: nothing below knows that the cells form a grid.  Each rank gets its
+    cells, the dofs they touch (owned first, ghosts after) and an ``IndexMap`` (ghost global
+    indices, ghost owners, ``index_to_dest_ranks``) in a rank-contiguous global numbering.
+
+    ``owner_rule``: a dof shared by several ranks is owned by the ``"lowest"`` of them (as in
+    ``partition_box``) or by a pseudo-random one (``"hash"``, so that ownership is not monotone
+    in the rank).  ``shuffle_seed`` (int): the local cell order, the order of the owned dofs and
+    the order of the ghosts are random permutations instead of the serial order - no run of
+    consecutive dof indices, no neighbouring consecutive cells survive.
+    Returns ``[Partition]`` for every rank."""
+    if np.isscalar(ncells):
+        ncells = (int(ncells),) * 3
+    ncells = tuple(int(v) for v in ncells)
+    cell_rank = np.asarray(cell_rank, dtype=np.int64).ravel()
+    assert cell_rank.size == int(np.prod(ncells))
+    nranks = int(cell_rank.max()) + 1
+    rng = np.random.default_rng(shuffle_seed) if shuffle_seed is not None else None
+    full = create_box(ncells, lengths, dtype=np.float64, perturb=perturb, seed=seed)
+    gdm = tensor_dofmap(full, P, order).astype(np.int64)  # serial dof ids
+    ntot = num_dofs(ncells, P)
+    Nd = gdm.shape[1]
+
+    # (dof, rank) incidences, unique
+    pairs = np.unique(gdm.ravel() * nranks + np.repeat(cell_rank, Nd))
+    pd, pr = pairs // nranks, pairs % nranks  # sorted by dof, ranks ascending within a dof
+    first = np.concatenate([[0], np.cumsum(np.bincount(pd, minlength=ntot))])  # CSR over dofs
+    cnt = np.diff(first)
+    if owner_rule == "lowest":
+        pick = np.zeros(ntot, dtype=np.int64)
+    elif owner_rule == "hash":
+        pick = (np.arange(ntot, dtype=np.int64) * 2654435761 >> 7) % cnt
+    else:
+        raise ValueError("owner_rule must be 'lowest' or 'hash'")
+    owner = pr[first[:-1] + pick]
+
+    # rank-contiguous global numbering: owned dofs of rank r in serial (or shuffled) order
+    new_global = np.empty(ntot, dtype=np.int64)
+    owned_lists, offsets = [], [0]
+    for r in range(nranks):
+        mine = np.nonzero(owner == r)[0]
+        if rng is not None:
+            mine = mine[rng.permutation(mine.size)]
+        owned_lists.append(mine)
+        new_global[mine] = offsets[-1] + np.arange(mine.size)
+        offsets.append(offsets[-1] + mine.size)
+
+    parts = []
+    for r in range(nranks):
+        cells = np.nonzero(cell_rank == r)[0]
+        if rng is not None:
+            cells = cells[rng.permutation(cells.size)]
+        mine = owned_lists[r]
+        nlocal = mine.size
+        touched = np.unique(gdm[cells])
+        gh = touched[owner[touched] != r]
+        gh = gh[rng.permutation(gh.size)] if rng is not None else gh[np.argsort(new_global[gh], kind="stable")]
+        local = np.full(ntot, -1, dtype=np.int64)
+        local[mine] = np.arange(nlocal)
+        local[gh] = nlocal + np.arange(gh.size)
+        dofmap = np.ascontiguousarray(local[gdm[cells]], dtype=np.int32)
+        assert dofmap.min() >= 0
+        l2s = np.concatenate([mine, gh]).astype(np.int64)
+        # destinations of every owned dof: the other ranks touching it, ascending
+        d_cnt = cnt[mine] - 1
+        d_off = np.concatenate([[0], np.cumsum(d_cnt)]).astype(np.int32)
+        d_arr = np.empty(int(d_off[-1]), dtype=np.int32)
+        sh = np.nonzero(d_cnt > 0)[0]
+        for i in sh:  # shared dofs only (a surface's worth)
+            rk = pr[first[mine[i]]:first[mine[i] + 1]]
+            d_arr[d_off[i]:d_off[i + 1]] = rk[rk != r]
+        imap = IndexMap(nlocal, ntot, (int(offsets[r]), int(offsets[r + 1])), new_global[gh].astype(np.int64),
+                        owner[gh].astype(np.int32), AdjacencyList(d_arr, d_off))
+        # geometry of the part: its vertices, renumbered
+        verts, inv = np.unique(full.x_dofs[cells], return_inverse=True)
+        mesh = BoxMesh((int(cells.size), 1, 1), np.ascontiguousarray(inv.reshape(-1, 8), dtype=np.int32),
+                       np.ascontiguousarray(full.x_g[verts], dtype=dtype), (0, 0, 0), ncells,
+                       tuple(float(v) for v in lengths), cells.astype(np.int64))
+        parts.append(Partition(r, nranks, mesh, dofmap, imap, new_global[l2s], l2s))
     return parts
 
 

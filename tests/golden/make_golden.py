@@ -2,7 +2,7 @@
 Golden-vector generator.  Run ONCE in the build container (it needs
 /root/reference and numba):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [--only-irregular]
 
 It imports the reference's own Python - ``numba-cpu/operators.py``,
 ``numba-cpu/sum_factorisation.py``, ``numba-cpu/scatterer.py``,
@@ -137,6 +137,71 @@ def load_ref(subdir, name, alias):
     return mod
 
 
+def scatter_case(name, parts, ncells, P, nranks, MPI, utils, scat):
+    """Index maps of ``parts`` through the reference's cuda/utils.py compute_scatterer_data and one
+    forward / reverse halo through its numba-cpu/scatterer.py -> scatter_<name>.npz."""
+    imaps = [p.index_map for p in parts]
+    res = run_ranks(nranks, lambda r: utils.compute_scatterer_data(imaps[r]))
+    store = {"nranks": nranks, "P": P, "ncells": np.array(ncells)}
+    for r, (od, gd) in enumerate(res):
+        im = imaps[r]
+        store[f"r{r}_size_local"] = im.size_local
+        store[f"r{r}_local_range"] = np.array(im.local_range)
+        store[f"r{r}_ghosts"] = im.ghosts
+        store[f"r{r}_owners"] = im.owners
+        store[f"r{r}_dest_array"] = im.index_to_dest_ranks().array
+        store[f"r{r}_dest_offsets"] = im.index_to_dest_ranks().offsets
+        store[f"r{r}_owners_ranks"] = np.asarray(od[2])
+        store[f"r{r}_owners_size"] = np.asarray(od[1])
+        store[f"r{r}_ghosts_ranks"] = np.asarray(gd[2])
+        store[f"r{r}_ghosts_size"] = np.asarray(gd[1])
+        for i, a_ in enumerate(od[0]):
+            store[f"r{r}_owners_idx{i}"] = np.asarray(a_, dtype=np.int64)
+        for i, a_ in enumerate(gd[0]):
+            store[f"r{r}_ghosts_idx{i}"] = np.asarray(a_, dtype=np.int64)
+
+    # halo exchange through numba-cpu/scatterer.py (4-tuple, flat indices)
+    rng = np.random.default_rng(11)
+    vecs = [rng.standard_normal(im.size_local + im.num_ghosts) for im in imaps]
+
+    def cpu_data(od, gd):
+        def flat(d):
+            idx = np.concatenate([np.asarray(v, np.int64) for v in d[0]]) if len(d[0]) else np.zeros(0, np.int64)
+            size = np.asarray(d[1], dtype=np.int64)
+            return [idx, size, np.insert(np.cumsum(size), 0, 0), np.asarray(d[2])]
+        return flat(od), flat(gd)
+
+    def do_rev(r):
+        od, gd = cpu_data(*res[r])
+        v = vecs[r].copy()
+        scat.scatter_reverse(MPI.COMM_WORLD, od, gd, imaps[r].size_local, np.float64)(v)
+        return v
+
+    def do_fwd(r):
+        od, gd = cpu_data(*res[r])
+        v = vecs[r].copy()
+        scat.scatter_forward(MPI.COMM_WORLD, od, gd, imaps[r].size_local, np.float64)(v)
+        return v
+
+    rev = run_ranks(nranks, do_rev)
+    fwd = run_ranks(nranks, do_fwd)
+    for r in range(nranks):
+        store[f"r{r}_vec"] = vecs[r]
+        store[f"r{r}_rev"] = rev[r]
+        store[f"r{r}_fwd"] = fwd[r]
+    np.savez_compressed(os.path.join(HERE, f"scatter_{name}.npz"), **store)
+    print(f"scatter {name}: ranks={nranks} ghosts={[im.num_ghosts for im in imaps]}")
+
+
+def irregular_scatter_cases(MPI, utils, scat):
+    """Unstructured-like partitions (substrate.partition_cells): blob-shaped parts, shuffled cell /
+    dof / ghost order, lowest-rank and pseudo-random ownership of the shared dofs."""
+    for name, ncells, P, nranks, rule in (("u5", (5, 4, 3), 2, 5, "hash"), ("u4", (4, 4, 3), 3, 4, "lowest")):
+        cr = S.blob_cell_ranks(ncells, nranks, seed=4)
+        parts = S.partition_cells(ncells, P, cr, shuffle_seed=7, owner_rule=rule)
+        scatter_case(name, parts, ncells, P, nranks, MPI, utils, scat)
+
+
 def main():
     MPI = install_stubs()
     sys.path.insert(0, os.path.join(REF, "numba-cpu"))  # `from sum_factorisation import ...`
@@ -144,6 +209,9 @@ def main():
     pre = load_ref("cuda", "precompute", "ref_precompute")
     utils = load_ref("cuda", "utils", "ref_utils")
     scat = load_ref("numba-cpu", "scatterer", "ref_scatterer")
+    if "--only-irregular" in sys.argv:  # add the unstructured-like fixtures without touching the others
+        irregular_scatter_cases(MPI, utils, scat)
+        return
 
     # ---------------- operators + geometry, P = 2..7, f32/f64 ---------------- #
     for P in range(2, 8):
@@ -204,58 +272,8 @@ def main():
     # ---------------- index maps + halo, 2x2x2 and 3x1x1 partitions ---------- #
     for name, ncells, P, nranks, grid in (("r8", (4, 4, 4), 2, 8, None), ("r3", (6, 2, 2), 3, 3, (3, 1, 1)),
                                           ("r2", (4, 3, 2), 4, 2, None)):
-        parts = S.partition_box(ncells, P, nranks, grid=grid)
-        imaps = [p.index_map for p in parts]
-        res = run_ranks(nranks, lambda r: utils.compute_scatterer_data(imaps[r]))
-        store = {"nranks": nranks, "P": P, "ncells": np.array(ncells)}
-        for r, (od, gd) in enumerate(res):
-            im = imaps[r]
-            store[f"r{r}_size_local"] = im.size_local
-            store[f"r{r}_local_range"] = np.array(im.local_range)
-            store[f"r{r}_ghosts"] = im.ghosts
-            store[f"r{r}_owners"] = im.owners
-            store[f"r{r}_dest_array"] = im.index_to_dest_ranks().array
-            store[f"r{r}_dest_offsets"] = im.index_to_dest_ranks().offsets
-            store[f"r{r}_owners_ranks"] = np.asarray(od[2])
-            store[f"r{r}_owners_size"] = np.asarray(od[1])
-            store[f"r{r}_ghosts_ranks"] = np.asarray(gd[2])
-            store[f"r{r}_ghosts_size"] = np.asarray(gd[1])
-            for i, a_ in enumerate(od[0]):
-                store[f"r{r}_owners_idx{i}"] = np.asarray(a_, dtype=np.int64)
-            for i, a_ in enumerate(gd[0]):
-                store[f"r{r}_ghosts_idx{i}"] = np.asarray(a_, dtype=np.int64)
-
-        # halo exchange through numba-cpu/scatterer.py (4-tuple, flat indices)
-        rng = np.random.default_rng(11)
-        vecs = [rng.standard_normal(im.size_local + im.num_ghosts) for im in imaps]
-
-        def cpu_data(od, gd):
-            def flat(d):
-                idx = np.concatenate([np.asarray(v, np.int64) for v in d[0]]) if len(d[0]) else np.zeros(0, np.int64)
-                size = np.asarray(d[1], dtype=np.int64)
-                return [idx, size, np.insert(np.cumsum(size), 0, 0), np.asarray(d[2])]
-            return flat(od), flat(gd)
-
-        def do_rev(r):
-            od, gd = cpu_data(*res[r])
-            v = vecs[r].copy()
-            scat.scatter_reverse(MPI.COMM_WORLD, od, gd, imaps[r].size_local, np.float64)(v)
-            return v
-
-        def do_fwd(r):
-            od, gd = cpu_data(*res[r])
-            v = vecs[r].copy()
-            scat.scatter_forward(MPI.COMM_WORLD, od, gd, imaps[r].size_local, np.float64)(v)
-            return v
-
-        rev = run_ranks(nranks, do_rev)
-        fwd = run_ranks(nranks, do_fwd)
-        for r in range(nranks):
-            store[f"r{r}_vec"] = vecs[r]
-            store[f"r{r}_rev"] = rev[r]
-            store[f"r{r}_fwd"] = fwd[r]
-        np.savez_compressed(os.path.join(HERE, f"scatter_{name}.npz"), **store)
-        print(f"scatter {name}: ranks={nranks} ghosts={[im.num_ghosts for im in imaps]}")
+        scatter_case(name, S.partition_box(ncells, P, nranks, grid=grid), ncells, P, nranks, MPI, utils, scat)
+    irregular_scatter_cases(MPI, utils, scat)
 
     # ---------------- linear RK4 loop with the reference operators ----------- #
     # Statement sequence of numba-cpu/demo_linear_box.py:322-382, 425-459,

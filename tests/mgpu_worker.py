@@ -93,6 +93,10 @@ def main():
         dict(workload="linear", P=4, n_per_rank=6, dtype="float64", nsteps=8, halo_kind="nccl"),
         dict(workload="westervelt", P=4, n_per_rank=5, dtype="float64", nsteps=6),
         dict(workload="linear", P=4, n_per_rank=6, dtype="float64", nsteps=12, integrator="leapfrog"),
+        # unstructured-like partitions: irregular parts, shuffled numbering, hash ownership
+        dict(workload="linear", P=4, n_per_rank=5, dtype="float64", nsteps=8, partition="blob"),
+        dict(workload="linear", P=3, n_per_rank=6, dtype="float64", nsteps=8, partition="blob", halo_kind="nccl"),
+        dict(workload="westervelt", P=3, n_per_rank=5, dtype="float64", nsteps=6, partition="blob"),
     ]
     if not a.quick:
         cases += [
@@ -106,6 +110,9 @@ def main():
             dict(workload="westervelt", P=6, n_per_rank=3, dtype="float64", nsteps=4),
             dict(workload="linear", P=2, n_per_rank=9, dtype="float64", nsteps=8),
             dict(workload="linear", P=7, n_per_rank=3, dtype="float64", nsteps=4),
+            dict(workload="linear", P=4, n_per_rank=5, dtype="float64", nsteps=12, integrator="leapfrog", partition="blob"),
+            dict(workload="linear", P=4, n_per_rank=5, dtype="float32", nsteps=8, partition="blob", split_mode="fused"),
+            dict(workload="westervelt_cells", P=3, n_per_rank=5, dtype="float64", nsteps=6, partition="blob"),
         ]
     results = []
     for c in cases:
@@ -114,7 +121,7 @@ def main():
         r = multi_gpu_parity(**c)
         results.append(r)
         if rank == 0:
-            print(f"[mgpu] {r['workload']} P{r['degree']} {r['dtype']} halo={r['halo']} geometry={r['geometry']} "
+            print(f"[mgpu] {r['workload']} P{r['degree']} {r['dtype']} {r['partition']} halo={r['halo']} geometry={r['geometry']} "
                   f"{r['integrator']} graph={r['graph']} split={r['split_mode']} iface={r['interface_cells']}: rel-L2 u {r['rel_l2_u']:.2e} v {r['rel_l2_v']:.2e} "
                   f"{'ok' if r['ok'] else 'FAIL'}", flush=True)
     sc = scatter_cases(rank, world)

@@ -51,7 +51,7 @@ def _lists(g, r, which):
     return [[g[f"r{r}_{which}_idx{i}"] for i in range(ranks.size)], g[f"r{r}_{which}_size"], ranks]
 
 
-@pytest.mark.parametrize("name", ["r2", "r3", "r8"])
+@pytest.mark.parametrize("name", ["r2", "r3", "r8", "u4", "u5"])
 def test_pack_unpack_kernels_vs_reference_fixture(golden_dir, name):
     """The reference's scatter, kernel for kernel (cuda/scatterer.py:139-188, 226-277), with the MPI
     round replaced by handing the send buffer to the receiver: pack_fwd -> unpack_fwd must reproduce
@@ -103,7 +103,7 @@ def test_pack_unpack_kernels_vs_reference_fixture(golden_dir, name):
     assert np.array_equal(b32.cpu().numpy(), g["r0_vec"].astype(np.float32)[gho[0][0][0]])
 
 
-@pytest.mark.parametrize("name", ["r2", "r3", "r8"])
+@pytest.mark.parametrize("name", ["r2", "r3", "r8", "u4", "u5"])
 def test_scatter_factories_vs_reference_fixture(golden_dir, name):
     """scatter_forward / scatter_reverse as the demos call them (cuda/demo_linear_box.py:206-207):
     ``scatter(buffer)`` modifies the vector in place."""
@@ -129,7 +129,7 @@ def test_scatter_factories_vs_reference_fixture(golden_dir, name):
         assert rel_l2(out[r][1], g[f"r{r}_rev"]) < 1e-15
 
 
-@pytest.mark.parametrize("name", ["r2", "r3", "r8"])
+@pytest.mark.parametrize("name", ["r2", "r3", "r8", "u4", "u5"])
 def test_p2p_halo_handle_vs_reference_fixture(golden_dir, name):
     """The fus_halo_* handle (epoch flags, put / get_add) on emulated ranks: forward twice in a
     row and reverse, against the numba-cpu fixture."""

@@ -149,7 +149,7 @@ def test_westervelt_rk4_vs_oracle(P, N, tag):
         assert rel_l2(s.v.cpu().numpy(), v_ref) < tol, mass_form
 
 
-@pytest.mark.parametrize("name", ["r2", "r3", "r8"])
+@pytest.mark.parametrize("name", ["r2", "r3", "r8", "u4", "u5"])
 def test_halo_exchange_vs_reference_fixture(golden_dir, name):
     """Forward and reverse halo through HaloExchange (ranks emulated by threads
     on one GPU) against what numba-cpu/scatterer.py produced."""

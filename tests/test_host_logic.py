@@ -26,7 +26,7 @@ def _index_maps(g):
     return maps
 
 
-@pytest.mark.parametrize("name", ["r2", "r3", "r8"])
+@pytest.mark.parametrize("name", ["r2", "r3", "r8", "u4", "u5"])
 def test_scatterer_data_bit_exact_vs_reference(golden_dir, name):
     """utils.compute_scatterer_data (vectorised) == cuda/utils.py:8-78 output."""
     g = np.load(os.path.join(golden_dir, f"scatter_{name}.npz"))
