@@ -141,7 +141,7 @@ WORKLOADS = {
 
 
 def build_problem(rank, world, n_per_gpu, dtype, halo_kind, workload="linear_box", degree=None, geometry="stream",
-                  split_cells=True, integrator="rk4"):
+                  split_cells=True, integrator="rk4", rank_grid=None, renumber_shared=True):
     """The demo's preamble through fenicsx_fus_gpu_b200.problem (device geometry,
     block partition, halo).  Returns the solver and an info dict."""
     from fenicsx_fus_gpu_b200 import problem
@@ -149,19 +149,21 @@ def build_problem(rank, world, n_per_gpu, dtype, halo_kind, workload="linear_box
 
     W = WORKLOADS[workload]
     deg = degree or W["P"]
-    grid = S.block_grid(world)
+    grid = tuple(rank_grid) if rank_grid else S.block_grid(world)
     ncells = tuple(n_per_gpu * g for g in grid)
     h = W["h"]  # the demo's cell size; the box grows with the rank grid
     lengths = tuple(h * n for n in ncells)
     used = halo_kind if world > 1 else "none"
     try:
-        su = problem.box_setup(deg, ncells, lengths, dtype, rank, world, grid=grid, halo_kind=halo_kind)
+        su = problem.box_setup(deg, ncells, lengths, dtype, rank, world, grid=grid, halo_kind=halo_kind,
+                               renumber_shared=renumber_shared)
     except Exception as e:  # peer memory unavailable on this box: NCCL send/recv round instead
         if halo_kind != "p2p" or world == 1:
             raise
         print(f"[bench] peer-memory halo unavailable ({e!r}); using the NCCL halo", file=sys.stderr, flush=True)
         used = "nccl"
-        su = problem.box_setup(deg, ncells, lengths, dtype, rank, world, grid=grid, halo_kind="nccl")
+        su = problem.box_setup(deg, ncells, lengths, dtype, rank, world, grid=grid, halo_kind="nccl",
+                               renumber_shared=renumber_shared)
 
     def make_solver(geometry="stream"):
         if workload == "linear_box":
@@ -181,7 +183,7 @@ def build_problem(rank, world, n_per_gpu, dtype, halo_kind, workload="linear_box
             split_cells=split_cells)
 
     solver = make_solver(geometry)
-    info = dict(make_solver=make_solver, ncells_local=su.mesh.num_cells, ndofs_local=su.ndofs, nlocal=su.nlocal, global_cells=ncells,
+    info = dict(rank_grid=list(grid), make_solver=make_solver, ncells_local=su.mesh.num_cells, ndofs_local=su.ndofs, nlocal=su.nlocal, global_cells=ncells,
                 global_dofs=su.global_dofs, grid=grid, h=h, detJ=su.dev["detJ"], tb=su.tables,
                 dofmap=su.dev["dofmap"], halo=used, degree=deg,
                 dt=problem.cfl_time_step(deg, h, W["c0"], W["f0"], W["cfl"]))
@@ -308,6 +310,9 @@ def main():
                          "or in the same launch behind an in-kernel wait (A/B, see solver.py)")
     ap.add_argument("--integrator", default="rk4", choices=["rk4", "leapfrog"],
                     help="rk4 (the reference's scheme, the headline) or leapfrog (one stiffness action per step)")
+    ap.add_argument("--rank-grid", default=None, help="AxBxC rank grid instead of the most cubic one (A/B runs)")
+    ap.add_argument("--no-renumber", action="store_true",
+                    help="keep the index map's numbering instead of moving the shared owned dofs to a contiguous tail (A/B)")
     ap.add_argument("--no-graph", action="store_true", help="launch the steps eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-kind", default=None, choices=["numba", "cpp", "port"], help="CPU arm implementation")
     ap.add_argument("--sustain-steps", type=int, default=250, help="steps of the extra >= 1 s sustained measurement")
@@ -445,7 +450,9 @@ def main():
 
     log("building the problem")
     solver, info = build_problem(rank, world, n_per_gpu, dtype, a.halo, a.workload, deg, a.geometry,
-                                 split_cells=not a.no_split, integrator=a.integrator)
+                                 split_cells=not a.no_split, integrator=a.integrator,
+                                 rank_grid=[int(v) for v in a.rank_grid.split("x")] if a.rank_grid else None,
+                                 renumber_shared=not a.no_renumber)
     config["integrator"] = a.integrator
     config["geometry"] = ("G streamed (reference data flow)" if a.geometry == "stream" else
                           f"auto: {solver.nrect} rectilinear + {solver.naff - solver.nrect} affine of {solver.ncells} "
@@ -454,7 +461,11 @@ def main():
                        "closes the shared dofs and puts the next stage input into the neighbours' ghost slots while "
                        f"the close of the non-shared dofs runs (split_mode={a.split_mode})",
                 "nccl": "NCCL send/recv", "none": "none (1 GPU)"}[info["halo"]]
-    config["parallelism"] = f"block partition x{world}, halo: {halo_txt}"
+    gtxt = "x".join(str(v) for v in ([int(v) for v in a.rank_grid.split("x")] if a.rank_grid else info["rank_grid"]))
+    config["parallelism"] = f"block partition x{world} (rank grid {gtxt}), halo: {halo_txt}"
+    if world > 1:
+        config["local_numbering"] = ("index map's own" if a.no_renumber else
+                                     "owned dofs that neighbours ghost moved to a contiguous tail (utils.shared_last_numbering)")
     if world > 1 and info["halo"] == "p2p":
         config["interface_cells_per_gpu"] = int(solver.ninterface)
         config["shared_dofs_per_gpu"] = int(solver.halo.nshared)

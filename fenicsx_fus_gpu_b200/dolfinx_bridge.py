@@ -81,7 +81,7 @@ def basix_tables(P: int, float_type, order: str = "basix"):
 
 
 def setup_from_dolfinx(mesh, V, basis_degree, float_type=np.float64, comm=None, halo_kind="nccl",
-                       tables=None, perm=None, max_halo_vecs=3) -> Setup:
+                       tables=None, perm=None, max_halo_vecs=3, renumber_shared=True) -> Setup:
     """``Setup`` of this rank from a DOLFINx ``mesh`` and function space ``V``
     (cuda/demo_linear_box.py:99-113, 175-207, 232-253).
 
@@ -106,8 +106,14 @@ def setup_from_dolfinx(mesh, V, basis_degree, float_type=np.float64, comm=None, 
     world = dist.get_world_size(comm) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(comm) if world > 1 else 0
     halo = None
+    lperm = None
     if world > 1:
         od, gd = utils.compute_scatterer_data(imap, comm)
+        if renumber_shared:
+            # private renumbering (shared owned dofs last, contiguous): Setup.local_perm maps a DOLFINx
+            # local index to the index the solver vectors use - u_dolfinx = sol.u[su.local_perm]
+            lperm, gd = utils.shared_last_numbering(nlocal, nghost, gd)
+            dofmap = np.ascontiguousarray(lperm[dofmap], dtype=np.int32)
         if halo_kind == "p2p":
             from .scatterer import P2PHaloExchange, SymmFabric
 
@@ -129,4 +135,4 @@ def setup_from_dolfinx(mesh, V, basis_degree, float_type=np.float64, comm=None, 
     h = float(np.sqrt(((cc[:, :, None, :] - cc[:, None, :, :]) ** 2).sum(-1)).max(axis=(1, 2)).min()) if num_cells else np.inf
     h = utils.global_min(h, comm)  # mesh_size of the reference: the minimum over all ranks
     return Setup(int(basis_degree), float_type, rank, world, HostMesh(x_dofs, x_g), tables, dofmap, nlocal + nghost,
-                 nlocal, int(imap.size_global), (num_cells,), halo, dev, h)
+                 nlocal, int(imap.size_global), (num_cells,), halo, dev, h, None, lperm)

@@ -48,6 +48,9 @@ class Setup:
     dev: dict = field(default_factory=dict)  # device tensors: dofmap, G, detJ, x_dofs, x_g, tables
     h: float = 0.0
     local_to_serial: np.ndarray | None = None  # (ndofs,) index of every local dof in the unpartitioned box
+    # multi-rank set-ups renumber the owned dofs so that the shared ones are contiguous
+    # (utils.shared_last_numbering): local_perm[index in the index map's numbering] = index used here
+    local_perm: np.ndarray | None = None
 
 
 def _d(a):
@@ -58,7 +61,7 @@ def _d(a):
 
 def box_setup(P, ncells, lengths, dtype=np.float64, rank=0, world=1, comm=None, grid=None,
               perturb=0.0, seed=0, order="basix", max_halo_vecs=3, scatter_data=None,
-              halo_kind="nccl", fabric=None, partition="block") -> Setup:
+              halo_kind="nccl", fabric=None, partition="block", renumber_shared=True) -> Setup:
     """Mesh part, dofmap, halo and device geometry of rank ``rank`` of ``world``.
 
     ``comm``: torch.distributed group / transport for the halo (None = world
@@ -66,7 +69,8 @@ def box_setup(P, ncells, lengths, dtype=np.float64, rank=0, world=1, comm=None, 
     rank grid) or ``"blob"`` - an unstructured-like partition (``substrate.partition_cells``:
     irregular connected parts, shuffled cell / dof / ghost order, pseudo-random ownership of
     the shared dofs), which exercises the generic index-map -> halo path the way a graph
-    partitioner's output would."""
+    partitioner's output would.  ``renumber_shared``: move the owned dofs that neighbours ghost
+    to the end of the owned block (``utils.shared_last_numbering``; ``Setup.local_perm``)."""
     import torch
 
     dtype = np.dtype(dtype)
@@ -78,6 +82,7 @@ def box_setup(P, ncells, lengths, dtype=np.float64, rank=0, world=1, comm=None, 
     tb = S.element_tables(P, order, dtype)
     halo = None
     l2s = None
+    lperm = None
     if world == 1:
         mesh = S.create_box(ncells, lengths, dtype=dtype, perturb=perturb, seed=seed)
         dofmap = S.tensor_dofmap(mesh, P, order)
@@ -100,6 +105,12 @@ def box_setup(P, ncells, lengths, dtype=np.float64, rank=0, world=1, comm=None, 
             od, gd = scatter_data
         else:
             od, gd = utils.compute_scatterer_data(part.index_map, comm)
+        if renumber_shared:
+            lperm, gd = utils.shared_last_numbering(nlocal, ndofs - nlocal, gd)
+            dofmap = np.ascontiguousarray(lperm[dofmap], dtype=np.int32)
+            moved = np.empty_like(l2s)
+            moved[lperm] = l2s
+            l2s = moved
         if halo_kind == "p2p":
             # halo fused into two kernels over NVLink peer memory (scatterer.P2PHaloExchange)
             if fabric is None:
@@ -117,7 +128,7 @@ def box_setup(P, ncells, lengths, dtype=np.float64, rank=0, world=1, comm=None, 
     pre.compute_geometry(dev["G"], dev["detJ"], (dev["x_dofs"], dev["x_g"]), nc, dev["dphi"], dev["wts"])
     h = min(lengths[i] / ncells[i] for i in range(3))
     return Setup(P, dtype, rank, world, mesh, tb, dofmap, ndofs, nlocal, S.num_dofs(ncells, P),
-                 tuple(ncells), halo, dev, h, l2s)
+                 tuple(ncells), halo, dev, h, l2s, lperm)
 
 
 def facet_group(su: Setup, local_facets, predicate=None):

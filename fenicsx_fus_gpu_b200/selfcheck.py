@@ -43,7 +43,7 @@ def _solver(su, workload, **kw):
 
 def multi_gpu_parity(P=4, n_per_rank=6, dtype=np.float64, nsteps=8, workload="linear", halo_kind="p2p",
                      use_graph=True, geometry="stream", perturb=0.1, split_cells=True, split_mode="none", integrator="rk4", group=None,
-                     partition="block"):
+                     partition="block", renumber_shared=True, grid=None):
     """rel-L2 of the partitioned solve against the single-GPU solve of the same global box.
     ``partition="blob"``: irregular parts with shuffled numbering (``problem.box_setup``) instead
     of the rank grid.
@@ -55,7 +55,7 @@ def multi_gpu_parity(P=4, n_per_rank=6, dtype=np.float64, nsteps=8, workload="li
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dtype = np.dtype(dtype)
-    grid = S.block_grid(world)
+    grid = tuple(grid) if grid is not None else S.block_grid(world)
     ncells = tuple(n_per_rank * g for g in grid)
     h = 0.12 / 80
     lengths = tuple(h * n for n in ncells)
@@ -67,7 +67,7 @@ def multi_gpu_parity(P=4, n_per_rank=6, dtype=np.float64, nsteps=8, workload="li
         dt = 0.5 * dt
 
     su = problem.box_setup(P, ncells, lengths, dtype, rank, world, comm=group, grid=grid, perturb=perturb, seed=7,
-                           halo_kind=halo_kind, partition=partition)
+                           halo_kind=halo_kind, partition=partition, renumber_shared=renumber_shared)
     sol = _solver(su, workload, split_cells=split_cells, **kw)
     sol.split_mode = split_mode
     sol.init()
@@ -80,7 +80,7 @@ def multi_gpu_parity(P=4, n_per_rank=6, dtype=np.float64, nsteps=8, workload="li
     parts = [None] * world
     dist.all_gather_object(parts, mine, group=group)
     out = dict(workload=workload, degree=P, dtype=dtype.name, n_gpus=world, global_cells=list(ncells),
-               global_dofs=int(su.global_dofs), steps=nsteps, halo=halo_kind, geometry=geometry, partition=partition, split_mode=split_mode, integrator=integrator,
+               global_dofs=int(su.global_dofs), steps=nsteps, halo=halo_kind, geometry=geometry, partition=partition, renumber_shared=bool(renumber_shared), rank_grid=list(grid), split_mode=split_mode, integrator=integrator,
                graph=bool(use_graph and sol._graph is not None), interface_cells=int(sol.ninterface),
                shared_dofs=int(getattr(sol.halo, "nshared", 0)), tol=TOL[dtype])
     res = [0.0, 0.0, 0.0]

@@ -157,6 +157,33 @@ def facet_integration_domain(facets, mesh):
     return boundary_data
 
 
+def shared_last_numbering(nlocal: int, nghost: int, ghosts_data):
+    """A local renumbering that puts the owned dofs other ranks ghost (the ``ghosts_data`` index
+    lists of ``compute_scatterer_data``) at the END of the owned block, contiguous and in their
+    old relative order; the other owned dofs keep their order in front, ghosts keep their indices.
+
+    Why: the fused solvers close those dofs in a separate kernel (after the reverse halo) beside
+    the bulk close.  In DOLFINx' numbering they are scattered - one 8-byte access per 32-byte
+    sector on a face normal to the fastest direction - and that scattered traffic is what slowed the
+    bulk close on the ranks that own faces (profiles/r02_multigpu_timeline.md).  Contiguous, the
+    shared block is a coalesced tail and the bulk close a plain prefix.  The index map (global
+    numbering, ghost order on the neighbours) is untouched: only this rank's private indices move.
+
+    Returns ``(perm, ghosts_data')``: ``perm[old] = new`` over ``nlocal + nghost`` entries and the
+    index lists in the new numbering (a new list; the sizes / ranks arrays are shared)."""
+    g_idx, g_size, g_ranks = ghosts_data
+    perm = np.arange(nlocal + nghost, dtype=np.int64)
+    lists = [np.asarray(ix, dtype=np.int64) for ix in g_idx]
+    if not lists or sum(a.size for a in lists) == 0:
+        return perm, ghosts_data
+    shared = np.zeros(nlocal, dtype=bool)
+    shared[np.concatenate(lists)] = True
+    ns = int(shared.sum())
+    perm[:nlocal][~shared] = np.arange(nlocal - ns, dtype=np.int64)
+    perm[:nlocal][shared] = nlocal - ns + np.arange(ns, dtype=np.int64)
+    return perm, [[perm[a] for a in lists], g_size, g_ranks]
+
+
 def colour_cells(connectivity, seed: int = 0) -> np.ndarray:
     """Greedy distance-1 colouring of the cells of a conforming mesh: no two
     cells of one colour share an entry of ``connectivity``.

@@ -97,6 +97,10 @@ def main():
         dict(workload="linear", P=4, n_per_rank=5, dtype="float64", nsteps=8, partition="blob"),
         dict(workload="linear", P=3, n_per_rank=6, dtype="float64", nsteps=8, partition="blob", halo_kind="nccl"),
         dict(workload="westervelt", P=3, n_per_rank=5, dtype="float64", nsteps=6, partition="blob"),
+        # the index map's own numbering (no shared-last renumbering); ranks split along z: the shared
+        # face is the scattered one
+        dict(workload="linear", P=4, n_per_rank=6, dtype="float64", nsteps=8, renumber_shared=False),
+        dict(workload="linear", P=4, n_per_rank=6, dtype="float64", nsteps=8, grid=(1, 1, world)),
     ]
     if not a.quick:
         cases += [

@@ -312,3 +312,108 @@ def test_operators_on_shuffled_numbering_vs_oracle():
         ops.mass_operator[1, 128](xd, cd, y2, dev(d.detJ), dm)
         assert rel_l2(y1.cpu().numpy(), yk) < tol
         assert rel_l2(y2.cpu().numpy(), ym) < tol
+
+
+# --------------------------------------------------------------------------- #
+# shared-last renumbering (utils.shared_last_numbering)
+# --------------------------------------------------------------------------- #
+def _renumbered(parts, sdata):
+    """What problem.box_setup does per rank: (dofmap, local_to_serial, owners_data, ghosts_data)
+    in the numbering with the shared owned dofs moved to a contiguous tail."""
+    out = []
+    for p, (od, gd) in zip(parts, sdata):
+        nl, ng = p.index_map.size_local, p.index_map.num_ghosts
+        perm, gd2 = utils.shared_last_numbering(nl, ng, gd)
+        l2s = np.empty_like(p.local_to_serial)
+        l2s[perm] = p.local_to_serial
+        out.append((np.ascontiguousarray(perm[p.dofmap], dtype=np.int32), l2s, od, gd2, perm))
+    return out
+
+
+@pytest.mark.parametrize("kind", ["box", "blob"])
+def test_shared_last_numbering_properties(kind):
+    N, P, R = (4, 4, 4), 2, 8
+    parts = (S.partition_box(N, P, R) if kind == "box" else
+             S.partition_cells(N, P, S.blob_cell_ranks(N, R, seed=2), shuffle_seed=1, owner_rule="hash"))
+    sdata = utils.compute_scatterer_data_all([p.index_map for p in parts])
+    for p, (od, gd), (dm, l2s, _, gd2, perm) in zip(parts, sdata, _renumbered(parts, sdata)):
+        nl, ng = p.index_map.size_local, p.index_map.num_ghosts
+        assert np.array_equal(np.sort(perm), np.arange(nl + ng))  # a permutation
+        assert np.array_equal(perm[nl:], np.arange(nl, nl + ng))  # ghosts stay
+        old = [np.asarray(a, np.int64) for a in gd[0]]
+        shared_old = np.unique(np.concatenate(old)) if old and sum(a.size for a in old) else np.zeros(0, np.int64)
+        ns = shared_old.size
+        # shared dofs: the tail of the owned block, old relative order kept; the rest: the head, order kept
+        assert np.array_equal(perm[shared_old], nl - ns + np.arange(ns))
+        rest = np.setdiff1d(np.arange(nl), shared_old)
+        assert np.array_equal(perm[rest], np.arange(nl - ns))
+        for a, b in zip(old, gd2[0]):
+            assert np.array_equal(perm[a], np.asarray(b))
+        # same serial dofs behind every dofmap entry
+        assert np.array_equal(l2s[dm], p.local_to_serial[p.dofmap])
+    # no neighbours: identity, lists untouched
+    perm, gd2 = utils.shared_last_numbering(10, 0, [[], np.zeros(0, np.int64), np.zeros(0, np.int32)])
+    assert np.array_equal(perm, np.arange(10)) and gd2[0] == []
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,halo", [("box", "p2p"), ("box", "nccl-shaped"), ("blob", "p2p")])
+def test_linear_rk4_with_shared_last_numbering_vs_serial_oracle(kind, halo):
+    """The partitioned solve in the renumbered local ordering (what problem.box_setup hands the
+    solvers on > 1 rank) against the single-rank oracle, ranks emulated on one GPU."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import problems
+    from fenicsx_fus_gpu_b200.scatterer import HaloExchange, LocalCluster, P2PHaloExchange, local_fabric
+    from fenicsx_fus_gpu_b200.solver import LinearSpectral3D, linear_source
+    from oracle import oracle as orc
+
+    dtt, P, N, L, R, nsteps = np.float64, 3, (4, 4, 4), (0.012, 0.01, 0.011), 8, 8
+    serial = problems.linear_problem(P, N, L, dtt, perturb=0.1, seed=11)
+    dt = problems.cfl_dt(P, min(L[i] / N[i] for i in range(3)), serial.c0, serial.f0)
+    m = np.zeros(serial.ndofs, dtt)
+    orc.mass_operator(np.ones(serial.ndofs, dtt), serial.cell_coeff1, m, serial.detJ, serial.dofmap)
+    prob = orc.LinearProblem(serial.P, serial.dofmap, serial.G, serial.tb.dphi_1D, serial.cell_coeff2, m,
+                             serial.bfacet_dofmap1, serial.detJ_f1, serial.facet_coeff1, serial.bfacet_dofmap2,
+                             serial.detJ_f2, serial.facet_coeff2, serial.f0, serial.p0, serial.c0)
+    u_ref, v_ref = np.zeros(serial.ndofs, dtt), np.zeros(serial.ndofs, dtt)
+    orc.linear_rk4(prob, u_ref, v_ref, 0.0, dt, nsteps)
+
+    if kind == "box":
+        parts = S.partition_box(N, P, R, lengths=L, dtype=dtt, perturb=0.1, seed=11)
+    else:
+        parts = S.partition_cells(N, P, S.blob_cell_ranks(N, R, seed=3), lengths=L, dtype=dtt, perturb=0.1, seed=11,
+                                  shuffle_seed=2, owner_rule="hash")
+    ren = _renumbered(parts, utils.compute_scatterer_data_all([p.index_map for p in parts]))
+    ndmax = max(q.index_map.size_local + q.index_map.num_ghosts for q in parts)
+
+    def body(r, transport):
+        p = parts[r]
+        dm, _, od, gd, _ = ren[r]
+        nl, ng = p.index_map.size_local, p.index_map.num_ghosts
+        d = problems.linear_problem(P, None, None, dtt, mesh=p.mesh, dofmap=dm, ndofs=nl + ng)
+        if halo == "p2p":
+            fab = local_fabric(transport.cluster, r, P2PHaloExchange.arena_bytes(ndmax, dtt))
+            h = P2PHaloExchange(fab, od, gd, nl, ng, dtt)
+            # the handle sees one contiguous block of shared dofs at the end of the owned range
+            assert h.nshared <= sum(len(a) for a in gd[0]) + 2
+        else:
+            h = HaloExchange(transport, od, gd, nl, dtt)
+        s = LinearSpectral3D(d.P, dtt, d.ndofs, d.dofmap, d.G, d.detJ, d.tb.dphi_1D, d.cell_coeff1, d.cell_coeff2,
+                             d.bfacet_dofmap1, d.detJ_f1, d.facet_coeff1, d.bfacet_dofmap2, d.detJ_f2, d.facet_coeff2,
+                             halo=h, source=lambda t: linear_source(t, d.f0, d.p0, d.c0), use_graph=False)
+        s.init()
+        s.rk4(0.0, dt, nsteps)
+        torch.cuda.synchronize()
+        return s.u.cpu().numpy(), s.v.cpu().numpy()
+
+    out = LocalCluster(R).run(body)
+    u, v = np.full_like(u_ref, np.nan), np.full_like(v_ref, np.nan)
+    for r, p in enumerate(parts):
+        nl = p.index_map.size_local
+        u[ren[r][1][:nl]] = out[r][0][:nl]
+        v[ren[r][1][:nl]] = out[r][1][:nl]
+    assert rel_l2(u, u_ref) < 1e-12
+    assert rel_l2(v, v_ref) < 1e-12
