@@ -78,7 +78,7 @@ def _sigs():
 #: every symbol include/fus_b200.h declares (checked by tests/test_abi.py)
 UNTYPED = ["fus_abi_version", "fus_last_error", "fus_launch_count", "fus_reset_launch_count",
            "fus_halo_pad_bytes", "fus_halo_create", "fus_halo_destroy", "fus_halo_num_shared",
-           "fus_halo_shared_mask", "fus_halo_status", "fus_halo_signal_reverse", "fus_halo_barrier",
+           "fus_halo_shared_mask", "fus_halo_shared_tail", "fus_halo_status", "fus_halo_signal_reverse", "fus_halo_barrier",
            "fus_halo_wait_reverse", "fus_stiffness_arm_halo_wait"]
 
 
@@ -121,6 +121,7 @@ def lib():
     lb.fus_halo_destroy.restype, lb.fus_halo_destroy.argtypes = I, [P]
     lb.fus_halo_num_shared.restype, lb.fus_halo_num_shared.argtypes = L, [P]
     lb.fus_halo_shared_mask.restype, lb.fus_halo_shared_mask.argtypes = P, [P]
+    lb.fus_halo_shared_tail.restype, lb.fus_halo_shared_tail.argtypes = L, [P]
     lb.fus_halo_status.restype, lb.fus_halo_status.argtypes = I, [P]
     lb.fus_halo_signal_reverse.restype, lb.fus_halo_signal_reverse.argtypes = I, [P, P]
     lb.fus_halo_barrier.restype, lb.fus_halo_barrier.argtypes = I, [P, P]

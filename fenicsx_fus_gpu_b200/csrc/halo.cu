@@ -36,6 +36,7 @@ struct fus_halo {
   FusHaloDev d;
   void* block = nullptr;  // one device allocation behind every table of `d`
   int device = 0;
+  long long shared_tail = -1;  // first dof of the close_shared set when it is the tail of the owned block
 };
 
 const FusHaloDev* fus_halo_dev_of(const fus_halo* h) { return &h->d; }
@@ -348,6 +349,10 @@ int fus_halo_create(const fus_halo_desc_t* desc, fus_halo_t** out) {
   d.useg = reinterpret_cast<const int*>(at(o_useg));
   d.upos = reinterpret_cast<const long long*>(at(o_upos));
   d.nu = (long long)uniq.size();
+  h->shared_tail = (!uniq.empty() && uniq.back() == desc->size_local - 1 &&
+                    uniq.back() - uniq.front() + 1 == (long long)uniq.size())
+                       ? uniq.front()
+                       : -1;
   d.shared_mask = at(o_mask);
   d.pad = static_cast<unsigned long long*>(desc->signal_pad);
   d.fwd_targets = reinterpret_cast<unsigned long long* const*>(at(o_fwd));
@@ -377,6 +382,7 @@ int fus_halo_destroy(fus_halo_t* h) {
 
 int64_t fus_halo_num_shared(const fus_halo_t* h) { return h ? h->d.nu : 0; }
 const uint8_t* fus_halo_shared_mask(const fus_halo_t* h) { return h ? h->d.shared_mask : nullptr; }
+int64_t fus_halo_shared_tail(const fus_halo_t* h) { return h ? h->shared_tail : -1; }
 
 int fus_halo_status(fus_halo_t* h) {
   FUS_NEED_HANDLE(h, "halo_status");

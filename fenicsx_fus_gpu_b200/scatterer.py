@@ -582,6 +582,9 @@ class P2PHaloExchange:
         self._lib = lib
         self.nshared = int(lib.fus_halo_num_shared(h))
         self.shared_mask = lib.fus_halo_shared_mask(h)  # device address of the bitmask
+        # >= 0: the shared dofs are the tail [shared_tail, N) of the owned block (utils.shared_last_numbering),
+        # so the bulk close is a plain prefix and needs no mask
+        self.shared_tail = int(lib.fus_halo_shared_tail(h))
         self._side = None
         self.use_side = True  # put the exchange kernels on a second stream (False: A/B measurements)
         fabric.host_barrier()  # every rank's pad and handle exist before the first signal
@@ -641,6 +644,14 @@ class P2PHaloExchange:
         gathers their partial sums itself (the solvers' fused close of the shared dofs)."""
         self.fabric.host_sync()
         check(self._lib.fus_halo_wait_reverse(self._h, current_stream()), "fus_halo_wait_reverse")
+
+    def bulk_close(self):
+        """Keyword arguments for the solvers' bulk close beside ``fus_rk_close_shared``: the prefix
+        ``n = shared_tail`` without a mask when the shared dofs are a contiguous tail, else the
+        whole owned block with the skip mask."""
+        if self.shared_tail >= 0:
+            return dict(n=self.shared_tail)
+        return dict(skip=self.shared_mask)
 
     def arm_stiffness_wait(self, first_interface_cell):
         """The next stiffness launch of this thread waits in-kernel, before its first interface

@@ -377,7 +377,7 @@ class _RK4:
     def _assemble(self, stage, g, dg, use_table, x, vn, wait=False):  # pragma: no cover - abstract
         raise NotImplementedError
 
-    def _close(self, stage, dt, count_step, base, acc, skip=None):  # pragma: no cover - abstract
+    def _close(self, stage, dt, count_step, base, acc, skip=None, n=None):  # pragma: no cover - abstract
         raise NotImplementedError
 
     def _close_shared(self, stage, dt, base, acc):  # pragma: no cover - abstract
@@ -469,7 +469,7 @@ class _RK4:
             with h.side():
                 h.wait_reverse()
                 self._close_shared(i, dt, base, acc)
-            self._close(i, dt, use_table, base, acc, skip=h.shared_mask)
+            self._close(i, dt, use_table, base, acc, **h.bulk_close())
             h.join()
 
     def begin_steps(self):
@@ -689,11 +689,11 @@ class LinearSpectral3D(_RK4):
         # b += K(-1/rho; un)                                  (cuda/demo_linear_box.py:543-545)
         self._probed(lambda: self._stiffness(x, wait))
 
-    def _close(self, stage, dt, count_step, base, acc, skip=None):
+    def _close(self, stage, dt, count_step, base, acc, skip=None, n=None):
         u, v, u0, v0, bdt, adt, mode = self._close_args(stage, dt, base, acc)
         check(fn("fus_rk_close", self.dtype)(
             u, v, u0, v0, self.ku.data_ptr(), None, self.un.data_ptr(), self.b.data_ptr(), self.m.data_ptr(),
-            bdt, adt, mode, self.nupd, self.step_dev.data_ptr() if count_step else None, skip, current_stream()),
+            bdt, adt, mode, self.nupd if n is None else n, self.step_dev.data_ptr() if count_step else None, skip, current_stream()),
             "fus_rk_close")
 
     def _close_shared(self, stage, dt, base, acc):
@@ -752,10 +752,10 @@ class LinearLeapfrog3D(LinearSpectral3D):
             self.halo.barrier()
             self.halo.put(*self._uv[0])
 
-    def _lf_close(self, m, dt_v, dt_u, count_step, skip=None):
+    def _lf_close(self, m, dt_v, dt_u, count_step, skip=None, n=None):
         u, v = self._uv[0]
         check(fn("fus_leapfrog_close", self.dtype)(
-            u.data_ptr(), v.data_ptr(), self.b.data_ptr(), m.data_ptr(), dt_v, dt_u, self.nupd,
+            u.data_ptr(), v.data_ptr(), self.b.data_ptr(), m.data_ptr(), dt_v, dt_u, self.nupd if n is None else n,
             self.step_dev.data_ptr() if count_step else None, skip, current_stream()), "fus_leapfrog_close")
 
     def _kick(self, t0, dt):
@@ -805,7 +805,7 @@ class LinearLeapfrog3D(LinearSpectral3D):
                 check(fn("fus_rk_close_shared", self.dtype)(
                     h.handle, 3, 1, 1, u.data_ptr(), v.data_ptr(), None, None, None, None, self.b.data_ptr(),
                     self._mlf.data_ptr(), None, None, None, dt, dt, 4, current_stream()), "fus_rk_close_shared")
-            self._lf_close(self._mlf, dt, dt, use_table, skip=h.shared_mask)
+            self._lf_close(self._mlf, dt, dt, use_table, **h.bulk_close())
             h.join()
             return
         if h is not None:
@@ -938,18 +938,19 @@ class WesterveltSpectral3D(_RK4):
                     xp, c3, vp, c4, c2, c5, mp, bp, sp(self.G, sg.g0), sp(self.detJ, sg.g0), dm, None, sg.n,
                     P, R, st), "fus_stiffness_westervelt")
 
-    def _close(self, stage, dt, count_step, base, acc, skip=None):
+    def _close(self, stage, dt, count_step, base, acc, skip=None, n=None):
         u, v, u0, v0, bdt, adt, mode = self._close_args(stage, dt, base, acc)
         step = self.step_dev.data_ptr() if count_step else None
+        n = self.nupd if n is None else n
         if not self._m_accum:
             check(fn("fus_rk_close_westervelt_pw", self.dtype)(
                 u, v, u0, v0, self.ku.data_ptr(), None, self.un.data_ptr(), self.b.data_ptr(), self.m0.data_ptr(),
-                self.m2.data_ptr(), self.m5.data_ptr(), bdt, adt, mode, self.nupd, step, skip, current_stream()),
+                self.m2.data_ptr(), self.m5.data_ptr(), bdt, adt, mode, n, step, skip, current_stream()),
                 "fus_rk_close_westervelt_pw")
             return
         check(fn("fus_rk_close_westervelt", self.dtype)(
             u, v, u0, v0, self.ku.data_ptr(), None, self.un.data_ptr(), self.b.data_ptr(), self.m.data_ptr(),
-            self.m0.data_ptr(), bdt, adt, mode, self.nupd, step, skip, current_stream()), "fus_rk_close_westervelt")
+            self.m0.data_ptr(), bdt, adt, mode, n, step, skip, current_stream()), "fus_rk_close_westervelt")
 
     def _close_shared(self, stage, dt, base, acc):
         u, v, u0, v0, bdt, adt, mode = self._close_args(stage, dt, base, acc)

@@ -277,6 +277,9 @@ int fus_halo_destroy(fus_halo_t* h);
  * as skip_mask (DEVICE pointer). */
 int64_t fus_halo_num_shared(const fus_halo_t* h);
 const uint8_t* fus_halo_shared_mask(const fus_halo_t* h);
+/* t >= 0 when those dofs are exactly the tail [t, size_local) of the owned block (the local numbering
+ * keeps the shared dofs last): fus_rk_close_* can then be given n = t and no mask.  -1 otherwise. */
+int64_t fus_halo_shared_tail(const fus_halo_t* h);
 /* 0, or FUS_ERR_HALO_TIMEOUT when a wait gave up (a neighbour never signalled). Synchronous. */
 int fus_halo_status(fus_halo_t* h);
 
