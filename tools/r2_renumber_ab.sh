@@ -1,6 +1,7 @@
 #!/bin/bash
 # A/B of the shared-last local renumbering on 2 GPUs: ranks split along z (the shared face is the
 # scattered one in the index map's numbering) and along x (already contiguous), with and without.
+# Usage: bash tools/r2_renumber_ab.sh [case ...]   (default: all four)
 mkdir -p gpurun_out/r2d
 run() {  # name, extra flags
   timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port $((29620 + RANDOM % 50)) \
@@ -17,7 +18,12 @@ except Exception as e:
     print(open(f"gpurun_out/r2d/{n}.err").read()[-1500:])
 PY
 }
-run z_renumber "--rank-grid 1x1x2"
-run z_plain "--rank-grid 1x1x2 --no-renumber"
-run x_renumber ""
-run x_plain "--no-renumber"
+want=${@:-z_renumber z_plain x_renumber x_plain}
+for c in $want; do
+  case $c in
+    z_renumber) run z_renumber "--rank-grid 1x1x2" ;;
+    z_plain) run z_plain "--rank-grid 1x1x2 --no-renumber" ;;
+    x_renumber) run x_renumber "" ;;
+    x_plain) run x_plain "--no-renumber" ;;
+  esac
+done
