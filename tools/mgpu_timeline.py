@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--out", default=None)
     ap.add_argument("--split-mode", default="none")
+    ap.add_argument("--rank-grid", default=None, help="AxBxC rank grid (default: the most cubic one)")
+    ap.add_argument("--no-renumber", action="store_true", help="keep the index map's local numbering")
     ap.add_argument("--fake-p2p", action="store_true",
                     help="1 GPU: a one-rank peer-memory halo (no neighbours) - vectors in the symmetric arena and the "
                          "skip mask passed to the close kernel, nothing exchanged: their cost in situ")
@@ -59,7 +61,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    out = {"n_gpus": world, "n": a.n}
+    out = {"n_gpus": world, "n": a.n, "rank_grid": a.rank_grid, "renumber_shared": not a.no_renumber}
     if a.fake_p2p:
         from fenicsx_fus_gpu_b200 import problem
         from fenicsx_fus_gpu_b200.scatterer import P2PHaloExchange, SymmFabric
@@ -75,7 +77,9 @@ def main():
         solver = problem.linear_solver(su, source_facets=[2], absorbing_facets=[3], p0=60000.0)
         info = {"dt": problem.cfl_time_step(4, h, 1500.0, 0.5e6, 0.65)}
     else:
-        solver, info = bench.build_problem(rank, world, a.n, np.float64, "p2p", "linear_box", 4, "stream")
+        solver, info = bench.build_problem(rank, world, a.n, np.float64, "p2p", "linear_box", 4, "stream",
+                                           rank_grid=[int(v) for v in a.rank_grid.split("x")] if a.rank_grid else None,
+                                           renumber_shared=not a.no_renumber)
     dt = info["dt"]
     solver.split_mode = a.split_mode
     out["graph_ms_per_step"] = timed_graph(solver, dt, a.steps)
