@@ -739,11 +739,13 @@ def partition_cells(
         # destinations of every owned dof: the other ranks touching it, ascending
         d_cnt = cnt[mine] - 1
         d_off = np.concatenate([[0], np.cumsum(d_cnt)]).astype(np.int32)
-        d_arr = np.empty(int(d_off[-1]), dtype=np.int32)
-        sh = np.nonzero(d_cnt > 0)[0]
-        for i in sh:  # shared dofs only (a surface's worth)
-            rk = pr[first[mine[i]]:first[mine[i] + 1]]
-            d_arr[d_off[i]:d_off[i + 1]] = rk[rk != r]
+        sh = np.nonzero(d_cnt > 0)[0]  # shared dofs only (a surface's worth)
+        c_sh = cnt[mine[sh]]  # incidences of each shared dof (its own rank included)
+        run0 = np.concatenate([[0], np.cumsum(c_sh)])[:-1]
+        at = np.repeat(first[mine[sh]] - run0, c_sh) + np.arange(int(c_sh.sum()))  # CSR rows, concatenated
+        rk = pr[at]
+        d_arr = rk[rk != r].astype(np.int32)  # rows stay in dof order, ranks ascending within a row
+        assert d_arr.size == int(d_off[-1])
         imap = IndexMap(nlocal, ntot, (int(offsets[r]), int(offsets[r + 1])), new_global[gh].astype(np.int64),
                         owner[gh].astype(np.int32), AdjacencyList(d_arr, d_off))
         # geometry of the part: its vertices, renumbered
