@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libfus_b200.so")
-SOURCES = ["api.cu", "stiffness.cu", "stiffness_affine.cu", "mass.cu", "vector.cu", "rk.cu", "geometry.cu", "halo.cu", "sampling.cu"]
+SOURCES = ["api.cu", "stiffness.cu", "stiffness_affine.cu", "stiffness_vertex.cu", "mass.cu", "vector.cu", "rk.cu", "geometry.cu", "halo.cu", "sampling.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 EXTRA = os.environ.get("FUS_NVCC_EXTRA", "").split()  # experiments, e.g. -DFUS_CFG_ALT
 # IEEE division / sqrt (no fast-math): parity with the reference is rel-L2 <= 1e-12 in f64

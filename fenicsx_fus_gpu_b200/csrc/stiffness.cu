@@ -244,11 +244,13 @@ extern "C" {
 
 int fus_set_dphi_f64(int P, const double* dphi, void* stream) {
   int rc = set_dphi<double>(P, dphi, static_cast<cudaStream_t>(stream));
-  return rc ? rc : fus_affine_set_dphi_f64(P, dphi, stream);  // the affine kernels' copy of the table
+  if (!rc) rc = fus_affine_set_dphi_f64(P, dphi, stream);  // the affine kernels' copy of the table
+  return rc ? rc : fus_vertex_set_dphi_f64(P, dphi, stream);
 }
 int fus_set_dphi_f32(int P, const float* dphi, void* stream) {
   int rc = set_dphi<float>(P, dphi, static_cast<cudaStream_t>(stream));
-  return rc ? rc : fus_affine_set_dphi_f32(P, dphi, stream);
+  if (!rc) rc = fus_affine_set_dphi_f32(P, dphi, stream);
+  return rc ? rc : fus_vertex_set_dphi_f32(P, dphi, stream);
 }
 
 int fus_stiffness_f64(const double* x, const double* coeff, double* y, const double* G,

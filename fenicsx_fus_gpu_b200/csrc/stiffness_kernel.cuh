@@ -14,6 +14,9 @@ __constant__ double c_K64[6][64];
 __constant__ float c_K32[6][64];
 __constant__ double c_W64[6][8];
 __constant__ float c_W32[6][8];
+// trilinear cells (GEO == 3): the 1-D quadrature points, in dof order (and the 1-D weights above)
+__constant__ double c_X64[6][8];
+__constant__ float c_X32[6][8];
 
 template <typename T, int P>
 struct DTable;
@@ -31,11 +34,13 @@ template <int P>
 struct KTable<double, P> {
   static __device__ __forceinline__ double at(int i) { return c_K64[P - 2][i]; }
   static __device__ __forceinline__ double w(int i) { return c_W64[P - 2][i]; }
+  static __device__ __forceinline__ double x(int i) { return c_X64[P - 2][i]; }
 };
 template <int P>
 struct KTable<float, P> {
   static __device__ __forceinline__ float at(int i) { return c_K32[P - 2][i]; }
   static __device__ __forceinline__ float w(int i) { return c_W32[P - 2][i]; }
+  static __device__ __forceinline__ float x(int i) { return c_X32[P - 2][i]; }
 };
 
 // cells per CTA batch / threads per CTA / min CTAs per SM, per (n, sizeof T)
@@ -90,6 +95,10 @@ struct Layout {
   static constexpr int TILE_Z = ((B * SCZ * S + 127) / 128) * 128;
   static constexpr int SMEM = BAR + kStages * STAGE + TILE_Y + TILE_Z;
   static constexpr int SMEM_AFF = BAR + TILE_Y + TILE_Z;  // affine cells: no G staging ring
+  // trilinear cells: 36 tangent coefficients per cell, two batches (this one, the next)
+  static constexpr int TCREC = 36;
+  static constexpr int TCBUF = ((B * TCREC * S + 127) / 128) * 128;
+  static constexpr int SMEM_TRI = SMEM_AFF + 2 * TCBUF;
 };
 
 template <typename T>
@@ -110,6 +119,10 @@ struct StiffArgs {
   const T* Gc;
   const T* wq;
   const T* detJc;
+  // trilinear-cell mode only: Tc[c, d, m, :] (36 values per cell), the tangent of reference
+  // direction d as a bilinear function of the other two coordinates (u, v):
+  //   t_d = Tc[d,0] + u Tc[d,1] + v Tc[d,2] + u v Tc[d,3]
+  const T* Tc;
   long long ncells;
   int bulk_ok;  // G base aligned for the 2-element vector loads of the AoS records
   // multi-GPU (WAIT instantiations): cells [wait_from, ncells) of this launch touch ghost dofs.
@@ -161,11 +174,21 @@ __device__ __forceinline__ G6<float> load_g6(const float* p) {
 //   constant 1-D stiffness matrix K1 = D^T diag(w1) D - one n x n product per pencil and
 //   direction, the y / z pencils are transformed in place (8 tile passes instead of 16, two
 //   barriers instead of five).
+// GEO 3 (trilinear): nothing is streamed but the dofmap and 36 coefficients per cell; the geometric
+//   factors are RECOMPUTED at every quadrature point from the cell's trilinear map.  Along the x
+//   pencil a thread owns, the tangent t_0 is constant and t_1, t_2 are affine in the pencil
+//   coordinate, so a point costs 6 FMAs for the tangents, three cross products c_a (the rows of
+//   adj J), det = t_0 . c_0, one division, and the product
+//       f_a = (w / |det|) c_a . (g_0 c_0 + g_1 c_1 + g_2 c_2)         ( = sum_b G_ab g_b )
+//   without ever forming G: ~60 flops per point against 6 streamed values.
 template <typename T, int n, int MODE, bool ATOMIC, int GEO, bool WAIT>
 __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
     stiffness_kernel(const StiffArgs<T> a) {
-  constexpr bool AFF = GEO >= 1;
+  constexpr bool TRI = GEO == 3;
+  constexpr bool AFF = GEO == 1 || GEO == 2;
+  constexpr bool NOSTREAM = GEO >= 1;  // no G ring (AFF or TRI)
   constexpr bool RECT = GEO == 2;
+  static_assert(!(TRI && MODE == 2), "trilinear mode: stiffness (MODE 0 / 1) only");
   constexpr bool DUAL = MODE >= 1;
   constexpr bool WEST = MODE == 2;
   using L = Layout<T, n>;
@@ -179,10 +202,12 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
 
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-  constexpr int RING = AFF ? 0 : kStages * L::STAGE;
+  constexpr int RING = NOSTREAM ? 0 : kStages * L::STAGE;
   unsigned char* stages = smem + L::BAR;
   T* UY = reinterpret_cast<T*>(smem + L::BAR + RING);
   T* UZ = reinterpret_cast<T*>(smem + L::BAR + RING + L::TILE_Y);
+  unsigned char* const tcb = smem + L::BAR + L::TILE_Y + L::TILE_Z;  // TRI: two coefficient buffers
+  (void)tcb;
 
   const int tid = threadIdx.x;
   const int cs = tid / N2;  // cell slot within the batch
@@ -200,7 +225,7 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
   const long long nb = (a.ncells + B - 1) / B;
   const long long stride = gridDim.x;
 
-  if constexpr (!AFF) {
+  if constexpr (!NOSTREAM) {
     if (tid == 0) {
 #pragma unroll
       for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
@@ -355,9 +380,41 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
     }
   };
 
+  // TRI: the coefficient records of a batch (B * 36 values, contiguous in Tc) are fetched one
+  // batch ahead by the first threads of the CTA, held in registers through the batch and stored
+  // into the other shared buffer at its end
+  constexpr int NTC = TRI ? (B * L::TCREC + THREADS - 1) / THREADS : 1;
+  T tcn[NTC];
+  (void)tcn;
+  auto load_tc = [&](long long b) {
+    if constexpr (TRI) {
+      const long long cell0 = b * B;
+      const long long lim = b < nb ? ((a.ncells - cell0) < (long long)B ? (a.ncells - cell0) : (long long)B) * L::TCREC : 0;
+#pragma unroll
+      for (int q = 0; q < NTC; ++q) {
+        const int idx = tid + q * THREADS;
+        tcn[q] = idx < lim ? __ldg(a.Tc + cell0 * L::TCREC + idx) : T(0);
+      }
+    }
+  };
+  auto store_tc = [&](int buf) {
+    if constexpr (TRI) {
+      T* dst = reinterpret_cast<T*>(tcb + buf * L::TCBUF);
+#pragma unroll
+      for (int q = 0; q < NTC; ++q) {
+        const int idx = tid + q * THREADS;
+        if (idx < B * L::TCREC) dst[idx] = tcn[q];
+      }
+    }
+  };
+
   // prologue: first batch of this CTA
   load_cell_scalars(blockIdx.x, csc);
-  if constexpr (!AFF) {
+  if constexpr (TRI) {
+    load_tc(blockIdx.x);
+    store_tc(0);  // visible after the first barrier of the loop
+  }
+  if constexpr (!NOSTREAM) {
     if (tid < 32 && (long long)blockIdx.x < nb && bulk_eligible(blockIdx.x)) issue(blockIdx.x, 0);
   }
   load_dofs(blockIdx.x, dof);
@@ -368,22 +425,23 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
   } else {
     load_x(dof, xv, xw);
   }
-  if constexpr (WEST && !AFF) load_detj(blockIdx.x, reinterpret_cast<T(&)[n]>(dj));
+  if constexpr (WEST && !NOSTREAM) load_detj(blockIdx.x, reinterpret_cast<T(&)[n]>(dj));
 
   int it = 0;
   for (long long b = blockIdx.x; b < nb; b += stride, ++it) {
     const int s = it & 1;
     const long long bn = b + stride;
     // TMA prefetch of the next batch into the other stage (consumed last iteration)
-    if constexpr (!AFF) {
+    if constexpr (!NOSTREAM) {
       if (tid < 32 && bn < nb && bulk_eligible(bn)) issue(bn, s ^ 1);
     }
+    load_tc(bn);
 
     unsigned char* st = stages + s * L::STAGE;
     const long long cell0 = b * B;
     const int ncur = (int)((a.ncells - cell0) < (long long)B ? (a.ncells - cell0) : (long long)B);
     const bool active = lane_ok && cs < ncur;
-    const bool bulk = !AFF && bulk_eligible(b);
+    const bool bulk = !NOSTREAM && bulk_eligible(b);
     const T* Gs = reinterpret_cast<const T*>(st + (bulk ? batch_shift(b) : 0u));
     G6<T> gc = {T(0), T(0), T(0), T(0), T(0), T(0)};  // affine mode: the cell's 6 factors (used after two barriers)
     T djc = T(0);
@@ -400,6 +458,8 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
         gc = {__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3), __ldg(p + 4), __ldg(p + 5)};
         if constexpr (WEST) djc = __ldg(a.detJc + cell0 + cs);
       }
+    } else if constexpr (TRI) {
+      // nothing per cell here: the coefficient records are in shared memory
     } else if (!bulk) {
       // tail batch / unaligned base: cooperative loads through the generic proxy
       const T* gsrc = a.G + cell0 * (long long)(Nd * 6);
@@ -419,7 +479,7 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
     } else {
       load_x(dofn, xvn, xwn);
     }
-    if constexpr (WEST && !AFF) load_detj(bn, reinterpret_cast<T(&)[n]>(djn));
+    if constexpr (WEST && !NOSTREAM) load_detj(bn, reinterpret_cast<T(&)[n]>(djn));
     load_cell_scalars(bn, cscn);
 
     // ---- x pencil (registers) -> tiles; x-direction gradient ----------------
@@ -552,22 +612,67 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
           ry[l] = T(0);
         }
       }
+      // TRI: the tangents along this thread's pencil (eta, zeta fixed; xi = X[i] varies):
+      //   t_0 constant,  t_1 = a1 + xi b1,  t_2 = a2 + xi b2
+      T t0[3], a1[3], b1[3], a2[3], b2[3];
+      T wab = T(0);
+      (void)t0;
+      (void)a1;
+      (void)b1;
+      (void)a2;
+      (void)b2;
+      (void)wab;
+      if constexpr (TRI) {
+        using KT = KTable<T, n - 1>;
+        const T* tc = reinterpret_cast<const T*>(tcb + (it & 1) * L::TCBUF) + cs * L::TCREC;
+        const T eta = KT::x(ra), zeta = KT::x(rb);
+        const T ez = eta * zeta;
+        wab = cc * (KT::w(ra) * KT::w(rb));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          t0[c] = tc[c] + eta * tc[3 + c] + zeta * tc[6 + c] + ez * tc[9 + c];
+          a1[c] = tc[12 + c] + zeta * tc[18 + c];
+          b1[c] = tc[15 + c] + zeta * tc[21 + c];
+          a2[c] = tc[24 + c] + eta * tc[30 + c];
+          b2[c] = tc[27 + c] + eta * tc[33 + c];
+        }
+      }
 #pragma unroll
       for (int i = 0; i < n; ++i) {
         const T wy = uy1[i * L::SPY];
         const T wz = uz1[i * L::SPZ];
-        G6<T> g;
-        T sc;
-        if constexpr (AFF) {
-          g = gc;
-          sc = cc * wreg[i];
+        T f0, f1, f2;
+        if constexpr (TRI) {
+          using KT = KTable<T, n - 1>;
+          const T xi = KT::x(i);
+          const T p0 = a1[0] + xi * b1[0], p1 = a1[1] + xi * b1[1], p2 = a1[2] + xi * b1[2];  // t_1
+          const T q0 = a2[0] + xi * b2[0], q1 = a2[1] + xi * b2[1], q2 = a2[2] + xi * b2[2];  // t_2
+          // rows of adj J: c0 = t1 x t2, c1 = t2 x t0, c2 = t0 x t1
+          const T c00 = p1 * q2 - p2 * q1, c01 = p2 * q0 - p0 * q2, c02 = p0 * q1 - p1 * q0;
+          const T c10 = q1 * t0[2] - q2 * t0[1], c11 = q2 * t0[0] - q0 * t0[2], c12 = q0 * t0[1] - q1 * t0[0];
+          const T c20 = t0[1] * p2 - t0[2] * p1, c21 = t0[2] * p0 - t0[0] * p2, c22 = t0[0] * p1 - t0[1] * p0;
+          const T det = t0[0] * c00 + t0[1] * c01 + t0[2] * c02;
+          const T sc = (wab * KT::w(i)) / fabs(det);
+          const T v0 = gx[i] * c00 + wy * c10 + wz * c20;
+          const T v1 = gx[i] * c01 + wy * c11 + wz * c21;
+          const T v2 = gx[i] * c02 + wy * c12 + wz * c22;
+          f0 = sc * (c00 * v0 + c01 * v1 + c02 * v2);
+          f1 = sc * (c10 * v0 + c11 * v1 + c12 * v2);
+          f2 = sc * (c20 * v0 + c21 * v1 + c22 * v2);
         } else {
-          g = load_g6(Gc + i * (N2 * 6));
-          sc = cc;
+          G6<T> g;
+          T sc;
+          if constexpr (AFF) {
+            g = gc;
+            sc = cc * wreg[i];
+          } else {
+            g = load_g6(Gc + i * (N2 * 6));
+            sc = cc;
+          }
+          f0 = sc * (g.g0 * gx[i] + g.g1 * wy + g.g2 * wz);
+          f1 = sc * (g.g1 * gx[i] + g.g3 * wy + g.g4 * wz);
+          f2 = sc * (g.g2 * gx[i] + g.g4 * wy + g.g5 * wz);
         }
-        const T f0 = sc * (g.g0 * gx[i] + g.g1 * wy + g.g2 * wz);
-        const T f1 = sc * (g.g1 * gx[i] + g.g3 * wy + g.g4 * wz);
-        const T f2 = sc * (g.g2 * gx[i] + g.g4 * wy + g.g5 * wz);
 #pragma unroll
         for (int l = 0; l < n; ++l) ry[l] += D::at(i * n + l) * f0;
         uy1[i * L::SPY] = f1;
@@ -619,8 +724,9 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
       dofn[i] = dofm[i];
       xv[i] = xvn[i];
       if constexpr (DUAL) xw[i] = xwn[i];
-      if constexpr (WEST && !AFF) dj[i] = djn[i];
+      if constexpr (WEST && !NOSTREAM) dj[i] = djn[i];
     }
+    store_tc((it + 1) & 1);  // next batch's coefficients (nobody reads that buffer any more)
     if constexpr (RECT) {
 #pragma unroll
       for (int q = 0; q < NCS; ++q) csc[q] = cscn[q];
@@ -632,7 +738,7 @@ __global__ void __launch_bounds__(Cfg<T, n>::THREADS, Cfg<T, n>::MINB)
 template <typename T, int n, int MODE, bool ATOMIC, int GEO, bool WAIT>
 int launch_one(const StiffArgs<T>& a, cudaStream_t stream) {
   using L = Layout<T, n>;
-  constexpr int SMEM = GEO ? L::SMEM_AFF : L::SMEM;
+  constexpr int SMEM = GEO == 3 ? L::SMEM_TRI : (GEO ? L::SMEM_AFF : L::SMEM);
   auto kern = stiffness_kernel<T, n, MODE, ATOMIC, GEO, WAIT>;
   // per instantiation AND per device: the shared-memory opt-in is a per-device attribute
   static int blocks_per_sm[64] = {0};

@@ -212,6 +212,49 @@ def stiffness_operator_rect(P, float_type):
     return _StiffnessRect(P, float_type)
 
 
+class _StiffnessVertex(_Kernel):
+    """The stiffness action with the geometric factors recomputed in the kernel from the cells'
+    trilinear maps (``csrc/stiffness_vertex.cu``): ``Tc`` from ``precompute.trilinear_coefficients``
+    takes the place of the ``G`` table - 36 values per cell instead of 6 n^3."""
+
+    def __init__(self, P: int, float_type):
+        if not 2 <= int(P) <= 7:
+            raise ValueError(f"stiffness_operator_vertex: degree {P} not in 2..7")
+        self.P, self.n, self.float_type = int(P), int(P) + 1, np.dtype(float_type)
+        _lib.sfx(self.float_type)
+
+    def __call__(self, x, entity_constants, y, Tc, points_1d, weights_1d, entity_dofmap, dphi):
+        T = self.float_type
+        xd, yd, cd, td = dev(x, T), dev(y, T), dev(entity_constants, T), dev(Tc, T)
+        dm = dev(entity_dofmap, np.int32)
+        nd3 = self.n**3
+        if len(dm.shape) != 2 or dm.shape[1] != nd3:
+            raise _lib.FusError(f"stiffness_operator_vertex: dofmap must be (ncells, {nd3}), got {dm.shape}")
+        if td.size != dm.shape[0] * 36 or cd.size != dm.shape[0]:
+            raise _lib.FusError("stiffness_operator_vertex: Tc (ncells, 36), constants (ncells,)")
+        if dm.shape[0] == 0:
+            raise ValueError("stiffness_operator_vertex: zero cells (empty launch)")
+        tabs = []
+        for name, a, size in (("dphi", dphi, self.n * self.n), ("points_1d", points_1d, self.n),
+                              ("weights_1d", weights_1d, self.n)):
+            if not isinstance(a, np.ndarray) or a.size != size:
+                raise _lib.FusError(f"stiffness_operator_vertex: {name} is a host table (numpy) of {size} entries")
+            tabs.append(np.ascontiguousarray(a, dtype=T))
+        D, x1, w1 = tabs
+        st = current_stream()
+        check(fn("fus_set_dphi", T)(self.P, D.ctypes.data, st), "fus_set_dphi")
+        check(fn("fus_set_vertex_tables", T)(self.P, x1.ctypes.data, w1.ctypes.data, st), "fus_set_vertex_tables")
+        check(fn("fus_stiffness_vertex", T)(xd.ptr, cd.ptr, yd.ptr, td.ptr, dm.ptr, None, dm.shape[0], self.P,
+                                            FUS_TABLES_RESIDENT, st), "fus_stiffness_vertex")
+
+
+def stiffness_operator_vertex(P, float_type):
+    """Stiffness kernel with on-the-fly geometry (not in the reference, which streams ``G``):
+    ``k[grid, block](x, constants, y, Tc, points_1d, weights_1d, dofmap, dphi_1D)``; ``Tc`` from
+    ``precompute.trilinear_coefficients``, the three tables on the host."""
+    return _StiffnessVertex(P, float_type)
+
+
 def stiffness_operator_affine(P, float_type):
     """Stiffness kernel for affine cells (not in the reference):
     ``k[grid, block](x, constants, y, Gc, weights, dofmap, dphi)``."""

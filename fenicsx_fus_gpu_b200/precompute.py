@@ -156,3 +156,47 @@ def compress_geometry(G, detJ, weights, tol=None):
                                          _ptr(detJc) if Jd is not None else None, _ptr(affine), nc, nq,
                                          float(tol), current_stream()), "fus_compress_geometry")
     return affine, Gc, detJc
+
+
+def trilinear_expansion(dphi, points):
+    """``M`` (3, 4, 8) float64 with ``dphi[d, q, :] = sum_m {1, u, v, u v}_m(points[q]) M[d, m, :]``,
+    ``(u, v)`` the two reference coordinates other than ``d``: the bilinear expansion of the
+    P1-geometry derivative table the reference tabulates from Basix (``cuda/demo_linear_box.py:232-239``).
+    Fitted by least squares from the table itself, so no vertex-order or basis convention is assumed;
+    raises when the table is not that of a trilinear map."""
+    dphi = np.asarray(dphi, dtype=np.float64)
+    pts = np.asarray(points, dtype=np.float64)
+    if dphi.ndim != 3 or dphi.shape[0] != 3 or dphi.shape[2] != 8 or pts.shape != (dphi.shape[1], 3):
+        raise _lib.FusError("trilinear_expansion: dphi (3, nq, 8) and points (nq, 3)")
+    M = np.zeros((3, 4, 8))
+    for d in range(3):
+        a, b = [c for c in range(3) if c != d]
+        u, v = pts[:, a], pts[:, b]
+        A = np.stack([np.ones_like(u), u, v, u * v], axis=1)
+        M[d] = np.linalg.lstsq(A, dphi[d], rcond=None)[0]
+        if np.abs(A @ M[d] - dphi[d]).max() > 1e-6 * max(1.0, np.abs(dphi[d]).max()):
+            raise _lib.FusError("trilinear_expansion: the derivative table is not that of a trilinear (8-vertex) geometry")
+    return M
+
+
+def trilinear_coefficients(mesh, num_cell, dphi, points, float_type=None):
+    """``Tc`` (num_cell, 36) device tensor: per cell the 3 x 4 coefficient vectors of its tangents
+    (``fus_trilinear_coeffs_*``; include/fus_b200.h) - what ``stiffness_operator_vertex`` takes in
+    place of the ``G`` table of ``compute_scaled_geometrical_factor``.  ``mesh = (x_dofs, x_g)`` as
+    for the other geometry functions (device arrays or numpy); ``dphi`` / ``points``: host tables."""
+    import torch
+
+    x_dofs, x_g = mesh
+    T = np.dtype(x_g.dtype) if isinstance(x_g, np.ndarray) else _lib.dev(x_g).dtype
+    if float_type is not None and np.dtype(float_type) != T:
+        raise _lib.FusError(f"trilinear_coefficients: x_g is {T}, expected {np.dtype(float_type)}")
+    if T not in (np.dtype(np.float64), np.dtype(np.float32)):
+        raise _lib.FusError(f"trilinear_coefficients: x_g must be float32 or float64, got {T}")
+    xg, _ = _to_dev(x_g, T)
+    xd, _ = _to_dev(x_dofs, np.int32)
+    tdt = torch.float64 if T == np.float64 else torch.float32
+    M = torch.from_numpy(np.ascontiguousarray(trilinear_expansion(dphi, points), dtype=T)).cuda()
+    Tc = torch.empty((int(num_cell), 36), dtype=tdt, device="cuda")
+    check(fn("fus_trilinear_coeffs", T)(_ptr(Tc), _ptr(xd), _ptr(xg), _ptr(M), int(num_cell), current_stream()),
+          "fus_trilinear_coeffs")
+    return Tc

@@ -171,6 +171,37 @@ int fus_stiffness2_rect_f32(const float* xa, const float* ca, const float* xb, c
                             float* y, const float* Gc, const int32_t* dofmap, const float* dphi,
                             int64_t ncells, int P, int flags, void* stream);
 
+/* Trilinear cells with the geometry recomputed in the kernel (the on-the-fly-geometry mode; replaces the
+ * G stream of cuda/operators.py:154-164 and the table cuda/precompute.py:115-163 fills): the map of a hexahedron
+ * with 8 vertices is trilinear, so the tangent dx/dxi_d is bilinear in the other two reference coordinates
+ * (u, v) = (eta, zeta), (xi, zeta), (xi, eta) for d = 0, 1, 2:
+ *     t_d = Tc[c,d,0,:] + u Tc[c,d,1,:] + v Tc[c,d,2,:] + u v Tc[c,d,3,:]
+ * fus_trilinear_coeffs_* : Tc (ncells, 3, 4, 3) = M (3, 4, 8) applied to the cell's vertex coordinates, where M is the
+ *     bilinear expansion of the P1 derivative table, dphi[d, q, v] = sum_m M[d, m, v] {1, u, v, u v}_m (pts[q])
+ *     (precompute.trilinear_expansion fits it from the same dphi / points cuda/precompute.py takes).
+ * fus_set_vertex_tables_* : the n 1-D quadrature points and weights in dof order (host or device).
+ * fus_stiffness_vertex_* / fus_stiffness2_vertex_* : y += K(coeff; x) / y += K(ca; xa) + K(cb; xb) with
+ *     G = w |det J| J^-1 J^-T rebuilt at every point (same result as fus_stiffness_* to rounding);
+ *     37 values per cell instead of 6 n^3 + 1. */
+int fus_trilinear_coeffs_f64(double* Tc, const int32_t* x_dofs, const double* x_g, const double* M,
+                             int64_t ncells, void* stream);
+int fus_trilinear_coeffs_f32(float* Tc, const int32_t* x_dofs, const float* x_g, const float* M,
+                             int64_t ncells, void* stream);
+int fus_set_vertex_tables_f64(int P, const double* x1, const double* w1, void* stream);
+int fus_set_vertex_tables_f32(int P, const float* x1, const float* w1, void* stream);
+int fus_stiffness_vertex_f64(const double* x, const double* coeff, double* y, const double* Tc,
+                             const int32_t* dofmap, const double* dphi, int64_t ncells, int P, int flags,
+                             void* stream);
+int fus_stiffness_vertex_f32(const float* x, const float* coeff, float* y, const float* Tc,
+                             const int32_t* dofmap, const float* dphi, int64_t ncells, int P, int flags,
+                             void* stream);
+int fus_stiffness2_vertex_f64(const double* xa, const double* ca, const double* xb, const double* cb,
+                              double* y, const double* Tc, const int32_t* dofmap, const double* dphi,
+                              int64_t ncells, int P, int flags, void* stream);
+int fus_stiffness2_vertex_f32(const float* xa, const float* ca, const float* xb, const float* cb, float* y,
+                              const float* Tc, const int32_t* dofmap, const float* dphi, int64_t ncells,
+                              int P, int flags, void* stream);
+
 /* Per cell: Gc[c,:] = mean_q G[c,q,:] / wq[q], detJc[c] = mean_q detJ[c,q] / wq[q] (detJ may be
  * NULL) and affine[c] = 1 when every G[c,q,:] / wq[q] (and detJ[c,q] / wq[q]) lies within
  * tol * max|Gc[c,:]| (tol * |detJc[c]|) of that mean, else 0.  One CTA per cell. */

@@ -111,6 +111,12 @@ def main():
             Kr = ops.stiffness_operator_rect(P, dt)
             f = lambda: Kr[Nc, (n, n, n)](x, c, y, Gc, tb.wts, dofmap, tb.dphi_1D)  # noqa: E731
             bytes_ = Nc * (Nd * 4 + 7 * s) + 2 * s * nd
+        elif op == "vertex":
+            # geometry recomputed in the kernel from 36 trilinear coefficients per cell (fus_stiffness_vertex)
+            Tc = pre.trilinear_coefficients((x_dofs, x_g), Nc, tb.dphi, tb.pts)
+            Kv = ops.stiffness_operator_vertex(P, dt)
+            f = lambda: Kv[Nc, (n, n, n)](x, c, y, Tc, tb.pts_1d, tb.wts_1d, dofmap, tb.dphi_1D)  # noqa: E731
+            bytes_ = Nc * (Nd * 4 + 37 * s) + 2 * s * nd
         elif op == "mass":
             f = lambda: ops.mass_operator[1, 128](x, c, y, detJ, dofmap)  # noqa: E731
             bytes_ = Nc * (Nd * (4 + s) + s) + 2 * s * nd
