@@ -75,6 +75,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", required=True)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default=None, help="run only the cases with this partition kind (e.g. blob), full list")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -118,6 +119,8 @@ def main():
             dict(workload="linear", P=4, n_per_rank=5, dtype="float32", nsteps=8, partition="blob", split_mode="fused"),
             dict(workload="westervelt_cells", P=3, n_per_rank=5, dtype="float64", nsteps=6, partition="blob"),
         ]
+    if a.only:
+        cases = [c for c in cases if c.get("partition", "block") == a.only]
     results = []
     for c in cases:
         c = dict(c)
